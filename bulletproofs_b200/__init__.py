@@ -1,0 +1,223 @@
+"""bulletproofs_b200 — Python harness over the C ABI of the B200-native Bulletproofs MSM engine.
+
+Everything here is a thin ctypes view of include/bpmsm.h (libbpmsm.so, hand-written sm_100a CUDA).
+There is no CPU path: importing works without a GPU (so the symbol table can be checked), but every
+compute call needs a B200 and raises otherwise.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbpmsm.so")
+
+TRANSCRIPT_BYTES = 203
+OK, ERR_INVALID_POINT, ERR_LENGTH_MISMATCH, ERR_NONCANONICAL_SCALAR, ERR_CUDA, ERR_INVALID_ARGUMENT = range(6)
+PROOF_OK, PROOF_VERIFICATION_ERROR, PROOF_FORMAT_ERROR, PROOF_INVALID_BITSIZE, PROOF_INVALID_GENERATORS_LENGTH, PROOF_INVALID_AGGREGATION = range(6)
+
+_c = ctypes
+_vp, _sz, _u8p, _int = _c.c_void_p, _c.c_size_t, _c.c_char_p, _c.c_int
+
+# every symbol include/bpmsm.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "bp_ctx_create": (_int, [_int, _vp, _c.POINTER(_vp)]),
+    "bp_ctx_destroy": (None, [_vp]),
+    "bp_last_error": (_c.c_char_p, [_vp]),
+    "bp_ctx_launch_count": (_c.c_uint64, [_vp]),
+    "bp_ctx_synchronize": (_int, [_vp]),
+    "bp_decompress_check_batch": (_int, [_vp, _u8p, _sz, _u8p]),
+    "bp_from_uniform_bytes_batch": (_int, [_vp, _u8p, _sz, _u8p]),
+    "bp_msm": (_int, [_vp, _u8p, _u8p, _sz, _u8p]),
+    "bp_msm_batch": (_int, [_vp, _u8p, _u8p, _c.POINTER(_c.c_uint64), _sz, _u8p, _u8p]),
+    "bp_msm_batch_device": (_int, [_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp]),
+    "bp_gens_create": (_int, [_vp, _sz, _sz, _c.POINTER(_vp)]),
+    "bp_gens_create_empty": (_int, [_vp, _sz, _sz, _c.POINTER(_vp)]),
+    "bp_gens_destroy": (None, [_vp]),
+    "bp_gens_get": (_int, [_vp, _int, _sz, _sz, _u8p]),
+    "bp_gens_device_table": (_int, [_vp, _c.POINTER(_vp), _c.POINTER(_sz)]),
+    "bp_rangeproof_verify_batch": (_int, [_vp, _vp, _u8p, _u8p, _sz, _u8p, _sz, _sz, _sz, _u8p, _u8p]),
+    "bp_rangeproof_verify_begin": (_int, [_vp, _vp, _u8p, _vp, _sz, _vp, _sz, _sz, _sz, _u8p]),
+    "bp_rangeproof_verify_finish": (_int, [_vp, _u8p]),
+    "bp_rangeproof_verify_batch_device": (_int, [_vp, _vp, _u8p, _vp, _sz, _vp, _sz, _sz, _sz, _u8p, _vp, _vp]),
+    "bp_transcript_new": (None, [_u8p, _sz, _u8p]),
+    "bp_transcript_append_message": (None, [_u8p, _u8p, _u8p, _sz]),
+    "bp_transcript_append_u64": (None, [_u8p, _u8p, _c.c_uint64]),
+    "bp_transcript_challenge_bytes": (None, [_u8p, _u8p, _u8p, _sz]),
+    "bp_debug_fe_op": (_int, [_vp, _int, _u8p, _u8p, _sz, _u8p]),
+}
+
+
+class BpError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__(f"bpmsm error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libbpmsm.so (loudly: a missing CUDA extension is an error, never a fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)          # AttributeError if the library does not export a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+class Transcript:
+    """merlin::Transcript on the 203-byte wire state (host helper of the C ABI)."""
+
+    def __init__(self, label: bytes = None, state: bytes = None):
+        self.state = ctypes.create_string_buffer(TRANSCRIPT_BYTES)
+        if state is not None:
+            self.state.raw = bytes(state)
+        else:
+            lib().bp_transcript_new(label, len(label), self.state)
+
+    def clone(self):
+        return Transcript(state=self.state.raw)
+
+    def append_message(self, label: bytes, msg: bytes):
+        lib().bp_transcript_append_message(self.state, label, msg, len(msg))
+
+    def append_u64(self, label: bytes, x: int):
+        lib().bp_transcript_append_u64(self.state, label, x)
+
+    def challenge_bytes(self, label: bytes, n: int) -> bytes:
+        out = ctypes.create_string_buffer(n)
+        lib().bp_transcript_challenge_bytes(self.state, label, out, n)
+        return out.raw
+
+    def to_bytes(self) -> bytes:
+        return self.state.raw
+
+
+class Context:
+    """One device + one CUDA stream (bp_ctx)."""
+
+    def __init__(self, device: int = 0, stream: int = None):
+        self._h = _vp()
+        rc = lib().bp_ctx_create(device, _vp(stream) if stream else None, ctypes.byref(self._h))
+        if rc != OK:
+            raise BpError(rc, "bp_ctx_create failed: no usable sm_100 CUDA device (there is no CPU fallback)")
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().bp_ctx_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != OK:
+            raise BpError(rc, lib().bp_last_error(self._h).decode())
+
+    @property
+    def launches(self) -> int:
+        return lib().bp_ctx_launch_count(self._h)
+
+    def synchronize(self):
+        self._check(lib().bp_ctx_synchronize(self._h))
+
+    # ---- group primitives
+    def decompress_check(self, points: bytes):
+        n = len(points) // 32
+        ok = ctypes.create_string_buffer(max(n, 1))
+        self._check(lib().bp_decompress_check_batch(self._h, points, n, ok))
+        return list(ok.raw[:n])
+
+    def from_uniform_bytes(self, uniform: bytes) -> bytes:
+        n = len(uniform) // 64
+        out = ctypes.create_string_buffer(32 * max(n, 1))
+        self._check(lib().bp_from_uniform_bytes_batch(self._h, uniform, n, out))
+        return out.raw[:32 * n]
+
+    # ---- MSM
+    def msm(self, scalars: bytes, points: bytes):
+        """RistrettoPoint::vartime_multiscalar_mul; returns (status, 32-byte compressed result)."""
+        if len(scalars) != len(points) or len(scalars) % 32:
+            raise BpError(ERR_LENGTH_MISMATCH, "scalars/points length mismatch")
+        out = ctypes.create_string_buffer(32)
+        rc = lib().bp_msm(self._h, scalars, points, len(scalars) // 32, out)
+        if rc in (ERR_CUDA, ERR_INVALID_ARGUMENT):
+            self._check(rc)
+        return rc, out.raw
+
+    def msm_batch(self, scalars: bytes, points: bytes, offsets):
+        n_msm = len(offsets) - 1
+        offs = (ctypes.c_uint64 * (n_msm + 1))(*offsets)
+        outs = ctypes.create_string_buffer(32 * n_msm)
+        status = ctypes.create_string_buffer(n_msm)
+        self._check(lib().bp_msm_batch(self._h, scalars, points, offs, n_msm, outs, status))
+        return list(status.raw), [outs.raw[32 * i:32 * i + 32] for i in range(n_msm)]
+
+    def debug_fe_op(self, op: int, a: bytes, b: bytes) -> bytes:
+        n = len(a) // 32
+        out = ctypes.create_string_buffer(32 * n)
+        self._check(lib().bp_debug_fe_op(self._h, op, a, b, n, out))
+        return out.raw
+
+
+class Gens:
+    """BulletproofGens::new(gens_capacity, party_capacity) + PedersenGens::default(), resident on the device."""
+
+    def __init__(self, ctx: Context, gens_capacity: int, party_capacity: int, empty: bool = False):
+        self.ctx, self.gens_capacity, self.party_capacity = ctx, gens_capacity, party_capacity
+        self._h = _vp()
+        fn = lib().bp_gens_create_empty if empty else lib().bp_gens_create
+        ctx._check(fn(ctx._h, gens_capacity, party_capacity, ctypes.byref(self._h)))
+
+    def get(self, which: int, party: int = 0, index: int = 0) -> bytes:
+        out = ctypes.create_string_buffer(32)
+        self.ctx._check(lib().bp_gens_get(self._h, which, party, index, out))
+        return out.raw
+
+    def G(self, party, index):
+        return self.get(0, party, index)
+
+    def H(self, party, index):
+        return self.get(1, party, index)
+
+    @property
+    def B(self):
+        return self.get(2)
+
+    @property
+    def B_blinding(self):
+        return self.get(3)
+
+    def device_table(self):
+        p, n = _vp(), _sz()
+        self.ctx._check(lib().bp_gens_device_table(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def close(self):
+        if self._h:
+            lib().bp_gens_destroy(self._h)
+            self._h = _vp()
+
+
+def rangeproof_size(n: int, m: int) -> int:
+    return 32 * (9 + 2 * ((n * m).bit_length() - 1))
+
+
+def verify_batch(ctx: Context, gens: Gens, transcript: Transcript, proofs: bytes, commitments: bytes, n: int, m: int,
+                 count: int, proof_len: int = None, seed: bytes = None):
+    """RangeProof::verify_multiple for `count` proofs; returns the list of per-proof verdict codes."""
+    if proof_len is None:
+        proof_len = len(proofs) // count
+    if len(proofs) != proof_len * count or len(commitments) != 32 * m * count:
+        raise BpError(ERR_LENGTH_MISMATCH, "proof/commitment buffer sizes")
+    verdicts = ctypes.create_string_buffer(count)
+    ctx._check(lib().bp_rangeproof_verify_batch(ctx._h, gens._h, transcript.to_bytes(), proofs, proof_len, commitments, n, m, count, seed, verdicts))
+    return list(verdicts.raw)

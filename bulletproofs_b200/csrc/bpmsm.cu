@@ -1,0 +1,515 @@
+// C ABI of the engine (include/bpmsm.h): context, scratch arenas, kernel orchestration.
+// No CPU fallback: every entry point needs a usable CUDA device and fails with BP_ERR_CUDA otherwise.
+#include <cuda_runtime.h>
+#include <sys/random.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "../../include/bpmsm.h"
+#include "kernels.cuh"
+
+static_assert(BP_TRANSCRIPT_BYTES == 203, "transcript wire size");
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr; size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct VerifyState {          // what bp_rangeproof_verify_begin leaves for _finish
+    bool active = false; rp_geom g{}; uint32_t count = 0; bp_gens *gens = nullptr;
+    const uint8_t *d_proofs = nullptr, *d_commitments = nullptr;
+};
+
+}  // namespace
+
+struct bp_ctx {
+    int device = 0; cudaStream_t stream = nullptr; bool own_stream = false;
+    std::string err; uint64_t launches = 0;
+    // MSM scratch
+    DevBuf in_scalars, in_points, in_offsets, niels, ok, msm_err, counts, starts, cursor, sorted, buckets, wsums, results, outs, flags;
+    // range-proof scratch
+    DevBuf rp_proofs, rp_commit, rp_tstate, rp_seed, rp_contrib, rp_scalars, rp_status, rp_pidx, rp_offsets, rp_verdict, rp_batch_ok;
+    DevBuf fb_scalars, fb_pidx, fb_offsets;
+    uint32_t *h_verdict = nullptr; size_t h_verdict_cap = 0;       // pinned
+    uint32_t *h_flag = nullptr;                                      // pinned, 4 words
+    VerifyState vs;
+};
+
+struct bp_gens {
+    bp_ctx *ctx = nullptr; size_t cap = 0, parties = 0, n_points = 0;
+    ge_niels *d_table = nullptr;       // [B_blinding, B, G[party][i].., H[party][i]..]
+};
+
+namespace {
+
+#define CK(ctx, call)                                                                                  \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return BP_ERR_CUDA; } } while (0)
+#define LAUNCH_CHECK(ctx)                                                                              \
+    do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e_); return BP_ERR_CUDA; } } while (0)
+
+inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
+
+// ---------------------------------------------------------------- host Keccak (SHAKE256 / SHA3-512) for the generator chain
+struct HostSponge {
+    uint64_t st[25]; unsigned rate, pos; uint8_t pad; bool squeezing;
+    HostSponge(unsigned r, uint8_t p) : rate(r), pos(0), pad(p), squeezing(false) { memset(st, 0, sizeof st); }
+    void xor_byte(unsigned i, uint8_t b) { st[i >> 3] ^= (uint64_t)b << (8 * (i & 7)); }
+    uint8_t get_byte(unsigned i) const { return (uint8_t)(st[i >> 3] >> (8 * (i & 7))); }
+    void absorb(const uint8_t *d, size_t n) { for (size_t i = 0; i < n; i++) { xor_byte(pos++, d[i]); if (pos == rate) { keccak_f1600(st); pos = 0; } } }
+    void squeeze(uint8_t *o, size_t n) {
+        if (!squeezing) { xor_byte(pos, pad); xor_byte(rate - 1, 0x80); keccak_f1600(st); pos = 0; squeezing = true; }
+        for (size_t i = 0; i < n; i++) { if (pos == rate) { keccak_f1600(st); pos = 0; } o[i] = get_byte(pos++); }
+    }
+};
+
+// ---------------------------------------------------------------- the Pippenger pipeline
+struct MsmArgs {
+    const uint8_t *d_scalars; const uint32_t *d_offsets; uint32_t n_msm, T;
+    const uint32_t *d_point_idx; const ge_niels *d_static, *d_dynamic; uint32_t *d_err; int window;
+};
+
+int msm_core(bp_ctx *ctx, const MsmArgs &a, ge_ext *d_results) {
+    if (a.T == 0) return BP_ERR_INVALID_ARGUMENT;
+    size_t avg = (a.T + a.n_msm - 1) / a.n_msm;
+    int c = a.window > 0 ? a.window : msm_pick_window(avg);
+    int W = msm_num_windows(c);
+    uint32_t nb = 1u << (c - 1);
+    size_t segs = (size_t)a.n_msm * W, n_buckets = segs * nb;
+    CK(ctx, ctx->counts.ensure(n_buckets * 4)); CK(ctx, ctx->starts.ensure(n_buckets * 4)); CK(ctx, ctx->cursor.ensure(n_buckets * 4));
+    CK(ctx, ctx->sorted.ensure((size_t)a.T * W * 4)); CK(ctx, ctx->buckets.ensure(n_buckets * sizeof(ge_ext))); CK(ctx, ctx->wsums.ensure(segs * sizeof(ge_ext)));
+    cudaStream_t s = ctx->stream;
+    CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, n_buckets * 4, s));
+    k_msm_count<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->counts.as<uint32_t>(), a.d_err);
+    LAUNCH_CHECK(ctx);
+    k_msm_scan<<<(unsigned)segs, 256, 0, s>>>(ctx->counts.as<uint32_t>(), nb, ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>());
+    LAUNCH_CHECK(ctx);
+    k_msm_scatter<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>());
+    LAUNCH_CHECK(ctx);
+    k_msm_accumulate<<<blocks_for(n_buckets, 128), 128, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(), a.d_offsets, W, nb,
+                                                                n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>());
+    LAUNCH_CHECK(ctx);
+    unsigned rthreads = nb >= 256 ? 256 : (nb < 32 ? 32 : nb);
+    k_msm_reduce<<<(unsigned)segs, rthreads, 0, s>>>(ctx->buckets.as<ge_ext>(), nb, ctx->wsums.as<ge_ext>());
+    LAUNCH_CHECK(ctx);
+    k_msm_combine<<<blocks_for(a.n_msm, 32), 32, 0, s>>>(ctx->wsums.as<ge_ext>(), a.n_msm, c, W, d_results);
+    LAUNCH_CHECK(ctx);
+    return BP_OK;
+}
+
+__global__ void k_mark_invalid(const uint8_t *ok, const uint32_t *offsets, uint32_t n_msm, uint32_t T, uint32_t *msm_err) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T || ok[t]) return;
+    atomicOr(msm_err + (n_msm == 1 ? 0u : msm_of_term(offsets, n_msm, t)), 1u);
+}
+__global__ void k_msm_status(const uint32_t *msm_err, uint32_t n_msm, uint8_t *status) {
+    uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_msm) return;
+    uint32_t e = msm_err[m];
+    status[m] = (e & 2u) ? BP_ERR_NONCANONICAL_SCALAR : (e & 1u) ? BP_ERR_INVALID_POINT : BP_OK;
+}
+__global__ void k_rp_point_idx(rp_geom g, uint32_t gens_cap, uint32_t gens_parties, uint32_t count, int per_proof_rows, uint32_t *out) {
+    // combined layout: [S static | count*D dynamic];  per-proof rows: count x [S static | D dynamic]
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = per_proof_rows ? (size_t)count * (g.S + g.D) : (size_t)g.S + (size_t)count * g.D;
+    if (i >= total) return;
+    uint32_t t, p = 0;
+    if (per_proof_rows) { p = (uint32_t)(i / (g.S + g.D)); t = (uint32_t)(i % (g.S + g.D)); } else t = (uint32_t)(i < g.S ? i : g.S);
+    uint32_t v;
+    if (t < 2) v = t;                                                                       // B_blinding, B
+    else if (t < 2 + g.N) { uint32_t q = t - 2; v = 2 + (q / g.n) * gens_cap + (q % g.n); } // G(n, m) iterator order (generators.rs:207-259)
+    else if (t < g.S) { uint32_t q = t - 2 - g.N; v = 2 + gens_parties * gens_cap + (q / g.n) * gens_cap + (q % g.n); }
+    else v = BP_POINT_DYNAMIC | (per_proof_rows ? (p * g.D + (t - g.S)) : (uint32_t)(i - g.S));
+    out[i] = v;
+}
+__global__ void k_fill_offsets(uint32_t n, uint32_t stride, uint32_t *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i <= n) out[i] = i * stride;
+}
+
+int lg2_exact(size_t v) { int k = 0; while (((size_t)1 << k) < v) k++; return ((size_t)1 << k) == v ? k : -1; }
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+int bp_ctx_create(int device, void *stream, bp_ctx **out) {
+    if (!out) return BP_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return BP_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return BP_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return BP_ERR_CUDA;   // sm_100a only
+    bp_ctx *c = new bp_ctx();
+    c->device = device;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return BP_ERR_CUDA; } c->own_stream = true; }
+    if (cudaMallocHost((void **)&c->h_flag, 64) != cudaSuccess) { delete c; return BP_ERR_CUDA; }
+    *out = c;
+    return BP_OK;
+}
+void bp_ctx_destroy(bp_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf *bufs[] = {&c->in_scalars, &c->in_points, &c->in_offsets, &c->niels, &c->ok, &c->msm_err, &c->counts, &c->starts, &c->cursor, &c->sorted, &c->buckets,
+                      &c->wsums, &c->results, &c->outs, &c->flags, &c->rp_proofs, &c->rp_commit, &c->rp_tstate, &c->rp_seed, &c->rp_contrib, &c->rp_scalars,
+                      &c->rp_status, &c->rp_pidx, &c->rp_offsets, &c->rp_verdict, &c->rp_batch_ok, &c->fb_scalars, &c->fb_pidx, &c->fb_offsets};
+    for (DevBuf *b : bufs) b->release();
+    if (c->h_verdict) cudaFreeHost(c->h_verdict);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+const char *bp_last_error(const bp_ctx *c) { return c ? c->err.c_str() : "null context"; }
+uint64_t bp_ctx_launch_count(const bp_ctx *c) { return c ? c->launches : 0; }
+int bp_ctx_synchronize(bp_ctx *c) { if (!c) return BP_ERR_INVALID_ARGUMENT; CK(c, cudaSetDevice(c->device)); CK(c, cudaStreamSynchronize(c->stream)); return BP_OK; }
+
+int bp_decompress_check_batch(bp_ctx *c, const uint8_t *points, size_t n, uint8_t *ok) {
+    if (!c || !points || !ok) return BP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return BP_OK;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->in_points.ensure(n * 32)); CK(c, c->niels.ensure(n * sizeof(ge_niels))); CK(c, c->ok.ensure(n));
+    CK(c, cudaMemcpyAsync(c->in_points.p, points, n * 32, cudaMemcpyHostToDevice, c->stream));
+    k_decompress<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, c->niels.as<ge_niels>(), c->ok.as<uint8_t>());
+    LAUNCH_CHECK(c);
+    CK(c, cudaMemcpyAsync(ok, c->ok.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return BP_OK;
+}
+
+int bp_from_uniform_bytes_batch(bp_ctx *c, const uint8_t *uniform, size_t n, uint8_t *points_out) {
+    if (!c || !uniform || !points_out) return BP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return BP_OK;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->in_points.ensure(n * 64)); CK(c, c->outs.ensure(n * 32));
+    CK(c, cudaMemcpyAsync(c->in_points.p, uniform, n * 64, cudaMemcpyHostToDevice, c->stream));
+    k_from_uniform<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, nullptr, c->outs.as<uint8_t>());
+    LAUNCH_CHECK(c);
+    CK(c, cudaMemcpyAsync(points_out, c->outs.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return BP_OK;
+}
+
+int bp_msm_batch_device(bp_ctx *c, const void *d_scalars, const void *d_points, const void *d_offsets_u32, size_t n_msm, size_t total_terms,
+                        void *d_outs, void *d_status) {
+    if (!c || !d_scalars || !d_points || !d_offsets_u32 || !d_outs || n_msm == 0) return BP_ERR_INVALID_ARGUMENT;
+    if (total_terms == 0 || total_terms >= (1u << 31) || n_msm >= (1u << 31)) return BP_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    uint32_t T = (uint32_t)total_terms, M = (uint32_t)n_msm;
+    CK(c, c->niels.ensure((size_t)T * sizeof(ge_niels))); CK(c, c->ok.ensure(T)); CK(c, c->msm_err.ensure((size_t)M * 4)); CK(c, c->results.ensure((size_t)M * sizeof(ge_ext)));
+    cudaStream_t s = c->stream;
+    CK(c, cudaMemsetAsync(c->msm_err.p, 0, (size_t)M * 4, s));
+    k_decompress<<<blocks_for(T, 128), 128, 0, s>>>((const uint8_t *)d_points, T, c->niels.as<ge_niels>(), c->ok.as<uint8_t>());
+    LAUNCH_CHECK(c);
+    k_mark_invalid<<<blocks_for(T, 256), 256, 0, s>>>(c->ok.as<uint8_t>(), (const uint32_t *)d_offsets_u32, M, T, c->msm_err.as<uint32_t>());
+    LAUNCH_CHECK(c);
+    MsmArgs a{(const uint8_t *)d_scalars, (const uint32_t *)d_offsets_u32, M, T, nullptr, nullptr, c->niels.as<ge_niels>(), c->msm_err.as<uint32_t>(), 0};
+    int rc = msm_core(c, a, c->results.as<ge_ext>());
+    if (rc) return rc;
+    k_compress<<<blocks_for(M, 128), 128, 0, s>>>(c->results.as<ge_ext>(), M, (uint8_t *)d_outs);
+    LAUNCH_CHECK(c);
+    if (d_status) { k_msm_status<<<blocks_for(M, 128), 128, 0, s>>>(c->msm_err.as<uint32_t>(), M, (uint8_t *)d_status); LAUNCH_CHECK(c); }
+    return BP_OK;
+}
+
+int bp_msm_batch(bp_ctx *c, const uint8_t *scalars, const uint8_t *points, const uint64_t *offsets, size_t n_msm, uint8_t *outs, uint8_t *status) {
+    if (!c || !offsets || !outs || n_msm == 0) return BP_ERR_INVALID_ARGUMENT;
+    size_t T = offsets[n_msm];
+    if (offsets[0] != 0 || T >= (1u << 31)) return BP_ERR_INVALID_ARGUMENT;
+    for (size_t j = 0; j < n_msm; j++) if (offsets[j + 1] < offsets[j]) return BP_ERR_LENGTH_MISMATCH;
+    CK(c, cudaSetDevice(c->device));
+    if (T == 0) {                      // every MSM empty: the identity encodes as 32 zero bytes
+        memset(outs, 0, 32 * n_msm); if (status) memset(status, 0, n_msm); return BP_OK;
+    }
+    if (!scalars || !points) return BP_ERR_INVALID_ARGUMENT;
+    std::vector<uint32_t> off32(n_msm + 1);
+    for (size_t j = 0; j <= n_msm; j++) off32[j] = (uint32_t)offsets[j];
+    CK(c, c->in_scalars.ensure(T * 32)); CK(c, c->in_points.ensure(T * 32)); CK(c, c->in_offsets.ensure((n_msm + 1) * 4));
+    CK(c, c->outs.ensure(n_msm * 32)); CK(c, c->flags.ensure(n_msm));
+    cudaStream_t s = c->stream;
+    CK(c, cudaMemcpyAsync(c->in_scalars.p, scalars, T * 32, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->in_points.p, points, T * 32, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->in_offsets.p, off32.data(), (n_msm + 1) * 4, cudaMemcpyHostToDevice, s));
+    int rc = bp_msm_batch_device(c, c->in_scalars.p, c->in_points.p, c->in_offsets.p, n_msm, T, c->outs.p, c->flags.p);
+    if (rc) return rc;
+    std::vector<uint8_t> st(n_msm);
+    CK(c, cudaMemcpyAsync(outs, c->outs.p, n_msm * 32, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaMemcpyAsync(st.data(), c->flags.p, n_msm, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    if (status) memcpy(status, st.data(), n_msm);
+    return BP_OK;
+}
+
+int bp_msm(bp_ctx *c, const uint8_t *scalars, const uint8_t *points, size_t n, uint8_t out[32]) {
+    uint64_t off[2] = {0, n}; uint8_t st = 0;
+    int rc = bp_msm_batch(c, scalars, points, off, 1, out, &st);
+    return rc ? rc : st;
+}
+
+// ---------------------------------------------------------------------------------------------- generators
+static int gens_alloc(bp_ctx *c, size_t cap, size_t parties, bp_gens **out) {
+    if (!c || !out || cap == 0 || parties == 0) return BP_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    bp_gens *g = new bp_gens();
+    g->ctx = c; g->cap = cap; g->parties = parties; g->n_points = 2 + 2 * cap * parties;
+    cudaError_t e = cudaMalloc((void **)&g->d_table, g->n_points * sizeof(ge_niels));
+    if (e != cudaSuccess) { c->err = std::string("cudaMalloc(gens): ") + cudaGetErrorString(e); delete g; return BP_ERR_CUDA; }
+    *out = g;
+    return BP_OK;
+}
+int bp_gens_create_empty(bp_ctx *c, size_t cap, size_t parties, bp_gens **out) { return gens_alloc(c, cap, parties, out); }
+
+int bp_gens_create(bp_ctx *c, size_t cap, size_t parties, bp_gens **out) {
+    int rc = gens_alloc(c, cap, parties, out);
+    if (rc) return rc;
+    bp_gens *g = *out;
+    // ristretto255 basepoint, compressed (RISTRETTO_BASEPOINT_COMPRESSED)
+    static const uint8_t BASEPOINT[32] = {0xe2, 0xf2, 0xae, 0x0a, 0x6a, 0xbc, 0x4e, 0x71, 0xa8, 0x84, 0xa9, 0x61, 0xc5, 0x00, 0x51, 0x5f,
+                                          0x58, 0xe3, 0x0b, 0x6a, 0xa5, 0x82, 0xdd, 0x8d, 0xb6, 0xa6, 0x59, 0x45, 0xe0, 0x8d, 0x2d, 0x76};
+    // uniform bytes: slot 0 = SHA3-512(B) for B_blinding (generators.rs:48-51); slot 1 unused (B is decompressed);
+    // then the SHAKE256("GeneratorsChain" || tag || LE32(party)) streams (generators.rs:62-104,179-204)
+    std::vector<uint8_t> uni(g->n_points * 64, 0);
+    { HostSponge h(72, 0x06); h.absorb(BASEPOINT, 32); h.squeeze(uni.data(), 64); }
+    for (int which = 0; which < 2; which++)
+        for (size_t p = 0; p < parties; p++) {
+            HostSponge h(136, 0x1f);
+            uint8_t label[5] = {(uint8_t)(which ? 'H' : 'G'), (uint8_t)p, (uint8_t)(p >> 8), (uint8_t)(p >> 16), (uint8_t)(p >> 24)};
+            h.absorb((const uint8_t *)"GeneratorsChain", 15); h.absorb(label, 5);
+            h.squeeze(uni.data() + 64 * (2 + (which * parties + p) * cap), 64 * cap);
+        }
+    CK(c, c->in_points.ensure(uni.size())); CK(c, c->in_scalars.ensure(32));
+    cudaStream_t s = c->stream;
+    CK(c, cudaMemcpyAsync(c->in_points.p, uni.data(), uni.size(), cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->in_scalars.p, BASEPOINT, 32, cudaMemcpyHostToDevice, s));
+    k_from_uniform<<<blocks_for(g->n_points, 128), 128, 0, s>>>(c->in_points.as<uint8_t>(), g->n_points, g->d_table, nullptr);
+    LAUNCH_CHECK(c);
+    k_decompress<<<1, 128, 0, s>>>(c->in_scalars.as<uint8_t>(), 1, g->d_table + 1, nullptr);
+    LAUNCH_CHECK(c);
+    CK(c, cudaStreamSynchronize(s));
+    return BP_OK;
+}
+void bp_gens_destroy(bp_gens *g) { if (!g) return; cudaSetDevice(g->ctx->device); cudaFree(g->d_table); delete g; }
+int bp_gens_device_table(bp_gens *g, void **d_table, size_t *bytes) {
+    if (!g || !d_table || !bytes) return BP_ERR_INVALID_ARGUMENT;
+    *d_table = g->d_table; *bytes = g->n_points * sizeof(ge_niels); return BP_OK;
+}
+int bp_gens_get(bp_gens *g, int which, size_t party, size_t index, uint8_t out[32]) {
+    if (!g || !out) return BP_ERR_INVALID_ARGUMENT;
+    bp_ctx *c = g->ctx; size_t slot;
+    if (which == 2) slot = 1; else if (which == 3) slot = 0;
+    else if ((which == 0 || which == 1) && party < g->parties && index < g->cap) slot = 2 + ((size_t)which * g->parties + party) * g->cap + index;
+    else return BP_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device)); CK(c, c->outs.ensure(32));
+    k_niels_to_compressed<<<1, 32, 0, c->stream>>>(g->d_table + slot, 1, c->outs.as<uint8_t>());
+    LAUNCH_CHECK(c);
+    CK(c, cudaMemcpyAsync(out, c->outs.p, 32, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return BP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- range proofs
+// Parameter checks of verify_multiple_with_rng (mod.rs:358-366) and of from_bytes / verification_scalars
+// that depend only on (proof_len, n, m): one verdict for the whole batch, or BP_PROOF_OK to go on.
+static uint8_t rp_param_verdict(const bp_gens *gens, size_t proof_len, size_t n, size_t m, rp_geom *g) {
+    if (proof_len % 32 != 0 || proof_len < 7 * 32) return BP_PROOF_FORMAT_ERROR;                 // mod.rs:498-503
+    size_t ne = (proof_len - 7 * 32) / 32;
+    if (ne < 2 || (ne - 2) % 2 != 0 || (ne - 2) / 2 >= 32) return BP_PROOF_FORMAT_ERROR;         // inner_product_proof.rs:375-388
+    size_t k = (ne - 2) / 2;
+    if (!(n == 8 || n == 16 || n == 32 || n == 64)) return BP_PROOF_INVALID_BITSIZE;
+    if (gens->cap < n || gens->parties < m) return BP_PROOF_INVALID_GENERATORS_LENGTH;
+    if (m == 0 || n * m != ((size_t)1 << k) || k > BP_MAX_LG_N) return BP_PROOF_VERIFICATION_ERROR;   // inner_product_proof.rs:204-211
+    g->n = (uint32_t)n; g->m = (uint32_t)m; g->k = (uint32_t)k; g->N = (uint32_t)(n * m);
+    g->D = (uint32_t)(4 + 2 * k + m); g->S = 2 + 2 * g->N; g->proof_len = (uint32_t)proof_len;
+    return BP_PROOF_OK;
+}
+
+// queue everything up to the verdicts; d_proofs / d_commitments are device pointers
+static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t count, const uint8_t *d_proofs, const uint8_t *d_commit,
+                           const uint8_t *h_transcript, const uint8_t *seed, uint32_t *d_verdict) {
+    cudaStream_t s = c->stream;
+    uint32_t T = g.S + count * g.D;
+    uint8_t seedbuf[32];
+    if (seed) memcpy(seedbuf, seed, 32);
+    else if (getrandom(seedbuf, 32, 0) != 32) { c->err = "getrandom failed"; return BP_ERR_CUDA; }
+    CK(c, c->rp_tstate.ensure(256)); CK(c, c->rp_seed.ensure(32));
+    CK(c, c->rp_contrib.ensure((size_t)count * g.S * sizeof(sc))); CK(c, c->rp_scalars.ensure((size_t)T * 32));
+    CK(c, c->rp_status.ensure((size_t)count * 4)); CK(c, c->niels.ensure((size_t)count * g.D * sizeof(ge_niels)));
+    CK(c, c->rp_pidx.ensure((size_t)T * 4)); CK(c, c->rp_offsets.ensure(8)); CK(c, c->results.ensure(sizeof(ge_ext)));
+    CK(c, c->flags.ensure(16)); CK(c, c->rp_batch_ok.ensure(4));
+    // small parameter uploads go through the pinned 64-byte scratch word? no: they are read before the call returns only when pageable,
+    // so stage them in the context's own pinned buffer
+    if (!c->h_verdict || c->h_verdict_cap < (size_t)count + 128) {
+        if (c->h_verdict) cudaFreeHost(c->h_verdict);
+        c->h_verdict = nullptr; c->h_verdict_cap = 0;
+        CK(c, cudaMallocHost((void **)&c->h_verdict, ((size_t)count + 128) * 4));
+        c->h_verdict_cap = (size_t)count + 128;
+    }
+    uint8_t *stage = reinterpret_cast<uint8_t *>(c->h_verdict + count);     // 512 pinned bytes behind the verdicts
+    memcpy(stage, h_transcript, BP_TRANSCRIPT_BYTES); memcpy(stage + 256, seedbuf, 32);
+    uint32_t offs[2] = {0, T}; memcpy(stage + 320, offs, 8);
+    uint32_t one = 1; memcpy(stage + 336, &one, 4);
+    CK(c, cudaMemcpyAsync(c->rp_tstate.p, stage, BP_TRANSCRIPT_BYTES, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->rp_seed.p, stage + 256, 32, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->rp_offsets.p, stage + 320, 8, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->rp_batch_ok.p, stage + 336, 4, cudaMemcpyHostToDevice, s));
+
+    uint8_t *d_scal = c->rp_scalars.as<uint8_t>();
+    k_rp_prep<<<count, 128, 0, s>>>(d_proofs, d_commit, g, c->rp_tstate.as<uint8_t>(), c->rp_seed.as<uint8_t>(), count, c->rp_contrib.as<sc>(),
+                                    d_scal + (size_t)g.S * 32, c->rp_status.as<uint32_t>());
+    LAUNCH_CHECK(c);
+    k_rp_decompress<<<blocks_for((size_t)count * g.D, 128), 128, 0, s>>>(d_proofs, d_commit, g, count, c->niels.as<ge_niels>(), c->rp_status.as<uint32_t>());
+    LAUNCH_CHECK(c);
+    k_rp_static_reduce<<<g.S, 128, 0, s>>>(c->rp_contrib.as<sc>(), g.S, count, d_scal);
+    LAUNCH_CHECK(c);
+    k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 0, c->rp_pidx.as<uint32_t>());
+    LAUNCH_CHECK(c);
+    MsmArgs a{d_scal, c->rp_offsets.as<uint32_t>(), 1, T, c->rp_pidx.as<uint32_t>(), gens->d_table, c->niels.as<ge_niels>(), nullptr, 0};
+    int rc = msm_core(c, a, c->results.as<ge_ext>());
+    if (rc) return rc;
+    k_is_identity<<<1, 32, 0, s>>>(c->results.as<ge_ext>(), 1, c->flags.as<uint32_t>());
+    LAUNCH_CHECK(c);
+    k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 0, count, d_verdict, c->rp_batch_ok.as<uint32_t>());
+    LAUNCH_CHECK(c);
+    return BP_OK;
+}
+
+// per-proof re-check after a failed combined check: count independent MSMs of S + D terms
+static int rp_verify_fallback(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t count, uint32_t *d_verdict) {
+    cudaStream_t s = c->stream;
+    uint32_t row = g.S + g.D; size_t T = (size_t)count * row;
+    if (T >= (1u << 31)) { c->err = "fallback batch too large"; return BP_ERR_INVALID_ARGUMENT; }
+    CK(c, c->fb_scalars.ensure(T * 32)); CK(c, c->fb_pidx.ensure(T * 4)); CK(c, c->fb_offsets.ensure(((size_t)count + 1) * 4));
+    CK(c, c->results.ensure((size_t)count * sizeof(ge_ext))); CK(c, c->flags.ensure((size_t)count * 4));
+    k_rp_expand_scalars<<<blocks_for(T, 128), 128, 0, s>>>(c->rp_contrib.as<sc>(), c->rp_scalars.as<uint8_t>() + (size_t)g.S * 32, g, count, c->fb_scalars.as<uint8_t>());
+    LAUNCH_CHECK(c);
+    k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 1, c->fb_pidx.as<uint32_t>());
+    LAUNCH_CHECK(c);
+    k_fill_offsets<<<blocks_for((size_t)count + 1, 256), 256, 0, s>>>(count, row, c->fb_offsets.as<uint32_t>());
+    LAUNCH_CHECK(c);
+    MsmArgs a{c->fb_scalars.as<uint8_t>(), c->fb_offsets.as<uint32_t>(), count, (uint32_t)T, c->fb_pidx.as<uint32_t>(), gens->d_table, c->niels.as<ge_niels>(), nullptr, 0};
+    int rc = msm_core(c, a, c->results.as<ge_ext>());
+    if (rc) return rc;
+    k_is_identity<<<blocks_for(count, 128), 128, 0, s>>>(c->results.as<ge_ext>(), count, c->flags.as<uint32_t>());
+    LAUNCH_CHECK(c);
+    k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 1, count, d_verdict, c->rp_batch_ok.as<uint32_t>());
+    LAUNCH_CHECK(c);
+    return BP_OK;
+}
+
+int bp_rangeproof_verify_begin(bp_ctx *c, bp_gens *gens, const uint8_t *transcript, const uint8_t *proofs, size_t proof_len, const uint8_t *commitments,
+                               size_t n, size_t m, size_t count, const uint8_t *seed) {
+    if (!c || !gens || !transcript || !proofs || !commitments || count == 0 || count >= (1u << 24)) return BP_ERR_INVALID_ARGUMENT;
+    if (c->vs.active) { c->err = "verify_begin called twice without verify_finish"; return BP_ERR_INVALID_ARGUMENT; }
+    CK(c, cudaSetDevice(c->device));
+    rp_geom g{};
+    uint8_t pv = rp_param_verdict(gens, proof_len, n, m, &g);
+    c->vs = VerifyState(); c->vs.active = true; c->vs.count = (uint32_t)count; c->vs.gens = gens; c->vs.g = g;
+    if (pv != BP_PROOF_OK) { c->vs.g.proof_len = 0; c->vs.g.n = pv; return BP_OK; }     // whole batch gets this verdict in _finish
+    if ((size_t)g.S + count * g.D >= (1u << 31)) { c->vs.active = false; return BP_ERR_INVALID_ARGUMENT; }
+    CK(c, c->rp_proofs.ensure(count * proof_len)); CK(c, c->rp_commit.ensure(count * m * 32)); CK(c, c->rp_verdict.ensure(count * 4));
+    CK(c, cudaMemcpyAsync(c->rp_proofs.p, proofs, count * proof_len, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->rp_commit.p, commitments, count * m * 32, cudaMemcpyHostToDevice, c->stream));
+    int rc = rp_verify_queue(c, gens, g, (uint32_t)count, c->rp_proofs.as<uint8_t>(), c->rp_commit.as<uint8_t>(), transcript, seed, c->rp_verdict.as<uint32_t>());
+    if (rc) { c->vs.active = false; return rc; }
+    CK(c, cudaMemcpyAsync(c->h_verdict, c->rp_verdict.p, count * 4, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(c->h_flag, c->flags.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    return BP_OK;
+}
+
+int bp_rangeproof_verify_finish(bp_ctx *c, uint8_t *verdicts) {
+    if (!c || !verdicts || !c->vs.active) return BP_ERR_INVALID_ARGUMENT;
+    VerifyState vs = c->vs; c->vs.active = false;
+    if (vs.g.proof_len == 0) { memset(verdicts, (int)vs.g.n, vs.count); return BP_OK; }
+    CK(c, cudaSetDevice(c->device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (c->h_flag[0] == 0) {            // combined check failed: find the offenders proof by proof
+        int rc = rp_verify_fallback(c, vs.gens, vs.g, vs.count, c->rp_verdict.as<uint32_t>());
+        if (rc) return rc;
+        CK(c, cudaMemcpyAsync(c->h_verdict, c->rp_verdict.p, (size_t)vs.count * 4, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+    }
+    for (uint32_t i = 0; i < vs.count; i++) verdicts[i] = (uint8_t)c->h_verdict[i];
+    return BP_OK;
+}
+
+int bp_rangeproof_verify_batch(bp_ctx *c, bp_gens *gens, const uint8_t *transcript, const uint8_t *proofs, size_t proof_len, const uint8_t *commitments,
+                               size_t n, size_t m, size_t count, const uint8_t *seed, uint8_t *verdicts) {
+    int rc = bp_rangeproof_verify_begin(c, gens, transcript, proofs, proof_len, commitments, n, m, count, seed);
+    if (rc) return rc;
+    return bp_rangeproof_verify_finish(c, verdicts);
+}
+
+int bp_rangeproof_verify_batch_device(bp_ctx *c, bp_gens *gens, const uint8_t *transcript, const void *d_proofs, size_t proof_len, const void *d_commitments,
+                                      size_t n, size_t m, size_t count, const uint8_t *seed, void *d_verdicts_u32, uint32_t *h_batch_ok_pinned) {
+    if (!c || !gens || !transcript || !d_proofs || !d_commitments || !d_verdicts_u32 || count == 0 || count >= (1u << 24)) return BP_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    rp_geom g{};
+    uint8_t pv = rp_param_verdict(gens, proof_len, n, m, &g);
+    if (pv != BP_PROOF_OK) return BP_ERR_INVALID_ARGUMENT;
+    if ((size_t)g.S + count * g.D >= (1u << 31)) return BP_ERR_INVALID_ARGUMENT;
+    int rc = rp_verify_queue(c, gens, g, (uint32_t)count, (const uint8_t *)d_proofs, (const uint8_t *)d_commitments, transcript, seed, (uint32_t *)d_verdicts_u32);
+    if (rc) return rc;
+    if (h_batch_ok_pinned) CK(c, cudaMemcpyAsync(h_batch_ok_pinned, c->rp_batch_ok.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    return BP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- host helpers
+// merlin::Transcript for hosts that do not have the Rust crate (the Python harness, C++ callers):
+// same STROBE code the device kernels use, compiled for the host.  Pure byte shuffling, no curve math.
+void bp_transcript_new(const uint8_t *label, size_t len, uint8_t out[BP_TRANSCRIPT_BYTES]) { merlin_t m; merlin_init(m, label, (uint32_t)len); merlin_store(out, m); }
+void bp_transcript_append_message(uint8_t state[BP_TRANSCRIPT_BYTES], const char *label, const uint8_t *msg, size_t len) {
+    merlin_t m; merlin_load(m, state); merlin_append(m, label, msg, (uint32_t)len); merlin_store(state, m);
+}
+void bp_transcript_append_u64(uint8_t state[BP_TRANSCRIPT_BYTES], const char *label, uint64_t x) { merlin_t m; merlin_load(m, state); merlin_append_u64(m, label, x); merlin_store(state, m); }
+void bp_transcript_challenge_bytes(uint8_t state[BP_TRANSCRIPT_BYTES], const char *label, uint8_t *out, size_t len) {
+    merlin_t m; merlin_load(m, state); merlin_challenge(m, label, out, (uint32_t)len); merlin_store(state, m);
+}
+
+// test hook: element-wise field operation on the device (pins the PTX carry chains of fe.cuh)
+__global__ void k_debug_fe(int op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t ab[32], bb[32]; ld32(ab, a + 32 * i); ld32(bb, b + 32 * i);
+    fe x = fe_frombytes_raw(ab), y = fe_frombytes_raw(bb), r;
+    switch (op) {
+        case 0: r = fe_add(x, y); break;
+        case 1: r = fe_sub(x, y); break;
+        case 2: r = fe_mul(x, y); break;
+        case 3: r = fe_invert(x); break;
+        case 4: r = fe_pow22523(x); break;
+        case 5: r = fe_neg(x); break;
+        case 7: r = fe_mul(fe_add(x, y), fe_sub(x, y)); break;      // chained, unreduced intermediates
+        default: r = fe_sq(x);
+    }
+    uint8_t o[32]; fe_tobytes(o, r); st32(out + 32 * i, o);
+}
+int bp_debug_fe_op(bp_ctx *c, int op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out) {
+    if (!c || !a || !b || !out || n == 0) return BP_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->in_scalars.ensure(n * 32)); CK(c, c->in_points.ensure(n * 32)); CK(c, c->outs.ensure(n * 32));
+    CK(c, cudaMemcpyAsync(c->in_scalars.p, a, n * 32, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaMemcpyAsync(c->in_points.p, b, n * 32, cudaMemcpyHostToDevice, c->stream));
+    k_debug_fe<<<blocks_for(n, 128), 128, 0, c->stream>>>(op, c->in_scalars.as<uint8_t>(), c->in_points.as<uint8_t>(), n, c->outs.as<uint8_t>());
+    LAUNCH_CHECK(c);
+    CK(c, cudaMemcpyAsync(out, c->outs.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return BP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,345 @@
+// Device kernels of the MSM engine (sm_100a).  One thread = one independent point / bucket /
+// scalar operation; a warp therefore carries 32 independent chains of the 8x32-bit-limb field
+// arithmetic in fe.cuh.  The work is integer-pipe bound (IMAD.WIDE), not HBM bound: one 64-byte
+// MSM term buys ~W mixed additions = W*7 field multiplications = W*7*72 wide multiplies.
+#pragma once
+#include <cuda_runtime.h>
+#include "ge.cuh"
+#include "sc.cuh"
+#include "merlin.cuh"
+#include "rp.cuh"
+#include "msm_common.cuh"
+
+#define BP_POINT_DYNAMIC 0x80000000u     // point_idx flag: index into the per-call (dynamic) point array
+
+// ------------------------------------------------------------------ vector load/store helpers
+__device__ __forceinline__ void ld32(uint8_t dst[32], const uint8_t *src) {       // 32 B, 16-B aligned
+    const uint4 *p = reinterpret_cast<const uint4 *>(src);
+    uint4 a = __ldg(p), b = __ldg(p + 1);
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    memcpy(dst, w, 32);
+}
+__device__ __forceinline__ void ld32_any(uint8_t dst[32], const uint8_t *src) {   // any alignment (proof bytes)
+    if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) { ld32(dst, src); return; }
+    if ((reinterpret_cast<uintptr_t>(src) & 3) == 0) { const uint32_t *p = reinterpret_cast<const uint32_t *>(src); uint32_t w[8]; for (int i = 0; i < 8; i++) w[i] = __ldg(p + i); memcpy(dst, w, 32); return; }
+    for (int i = 0; i < 32; i++) dst[i] = src[i];
+}
+__device__ __forceinline__ void st32(uint8_t *dst, const uint8_t src[32]) {
+    uint32_t w[8]; memcpy(w, src, 32);
+    uint4 *p = reinterpret_cast<uint4 *>(dst);
+    p[0] = make_uint4(w[0], w[1], w[2], w[3]); p[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+__device__ __forceinline__ fe ld_fe(const fe *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p); uint4 a = q[0], b = q[1];
+    fe r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w; return r;
+}
+__device__ __forceinline__ fe ldg_fe(const fe *p) {
+    const uint4 *q = reinterpret_cast<const uint4 *>(p); uint4 a = __ldg(q), b = __ldg(q + 1);
+    fe r; r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w; return r;
+}
+__device__ __forceinline__ void st_fe(fe *p, const fe &v) {
+    uint4 *q = reinterpret_cast<uint4 *>(p);
+    q[0] = make_uint4(v.v[0], v.v[1], v.v[2], v.v[3]); q[1] = make_uint4(v.v[4], v.v[5], v.v[6], v.v[7]);
+}
+__device__ __forceinline__ ge_niels ldg_niels(const ge_niels *p) { ge_niels r; r.ypx = ldg_fe(&p->ypx); r.ymx = ldg_fe(&p->ymx); r.xy2d = ldg_fe(&p->xy2d); return r; }
+__device__ __forceinline__ void st_niels(ge_niels *p, const ge_niels &v) { st_fe(&p->ypx, v.ypx); st_fe(&p->ymx, v.ymx); st_fe(&p->xy2d, v.xy2d); }
+__device__ __forceinline__ ge_ext ld_ext(const ge_ext *p) { ge_ext r; r.X = ld_fe(&p->X); r.Y = ld_fe(&p->Y); r.Z = ld_fe(&p->Z); r.T = ld_fe(&p->T); return r; }
+__device__ __forceinline__ void st_ext(ge_ext *p, const ge_ext &v) { st_fe(&p->X, v.X); st_fe(&p->Y, v.Y); st_fe(&p->Z, v.Z); st_fe(&p->T, v.T); }
+
+__device__ __forceinline__ ge_ext shfl_down_ext(const ge_ext &p, int d) {
+    ge_ext r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        r.X.v[i] = __shfl_down_sync(0xffffffffu, p.X.v[i], d); r.Y.v[i] = __shfl_down_sync(0xffffffffu, p.Y.v[i], d);
+        r.Z.v[i] = __shfl_down_sync(0xffffffffu, p.Z.v[i], d); r.T.v[i] = __shfl_down_sync(0xffffffffu, p.T.v[i], d);
+    }
+    return r;
+}
+
+// ------------------------------------------------------------------ K1: batched Ristretto decompress
+// in: n x 32 B compressed.  out: n affine-Niels points (identity when invalid), ok[i] in {0,1}.
+__global__ void __launch_bounds__(128) k_decompress(const uint8_t *__restrict__ in, size_t n, ge_niels *__restrict__ out, uint8_t *__restrict__ ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t s[32]; ld32(s, in + 32 * i);
+    fe x, y; bool valid = ge_decode(x, y, s);
+    ge_niels q = valid ? ge_to_niels_affine(x, y) : ge_niels_identity();
+    st_niels(out + i, q);
+    if (ok) ok[i] = valid ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ K3: batched compress / identity test
+__global__ void __launch_bounds__(128) k_compress(const ge_ext *__restrict__ in, size_t n, uint8_t *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t s[32]; ge_encode(s, ld_ext(in + i)); st32(out + 32 * i, s);
+}
+__global__ void k_is_identity(const ge_ext *__restrict__ in, size_t n, uint32_t *__restrict__ flags) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = ge_is_identity(ld_ext(in + i)) ? 1u : 0u;
+}
+
+// ------------------------------------------------------------------ K7: from_uniform_bytes (generator chain)
+// in: n x 64 B.  out: affine-Niels table entry and/or compressed bytes.
+__global__ void __launch_bounds__(128) k_from_uniform(const uint8_t *__restrict__ in, size_t n, ge_niels *__restrict__ out_niels, uint8_t *__restrict__ out_comp) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t u[64]; ld32(u, in + 64 * i); ld32(u + 32, in + 64 * i + 32);
+    ge_ext p = ge_from_uniform(u);
+    if (out_comp) { uint8_t s[32]; ge_encode(s, p); st32(out_comp + 32 * i, s); }
+    if (out_niels) { fe zi = fe_invert(p.Z); st_niels(out_niels + i, ge_to_niels_affine(fe_mul(p.X, zi), fe_mul(p.Y, zi))); }
+}
+// extended -> affine Niels (one inversion per point); used after the IPP generator fold
+__global__ void __launch_bounds__(128) k_ext_to_niels(const ge_ext *__restrict__ in, size_t n, ge_niels *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_ext p = ld_ext(in + i); fe zi = fe_invert(p.Z);
+    st_niels(out + i, ge_to_niels_affine(fe_mul(p.X, zi), fe_mul(p.Y, zi)));
+}
+__global__ void __launch_bounds__(128) k_niels_to_compressed(const ge_niels *__restrict__ in, size_t n, uint8_t *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t s[32]; ge_encode(s, ge_from_niels(ldg_niels(in + i))); st32(out + 32 * i, s);
+}
+
+// ------------------------------------------------------------------ K2: Pippenger bucket pipeline
+// A batch of n_msm MSMs over a flat term array.  "segment" = (msm, window); every segment owns nb =
+// 2^(c-1) buckets and a slice of `sorted` with room for all terms of its MSM:
+//     seg = msm*W + w,   slice base = W*offsets[msm] + w*(offsets[msm+1]-offsets[msm]).
+__device__ __forceinline__ uint32_t msm_of_term(const uint32_t *__restrict__ offsets, uint32_t n_msm, uint32_t t) {
+    uint32_t lo = 0, hi = n_msm;            // largest j with offsets[j] <= t
+    while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(offsets + mid) <= t) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// pass 1: histogram.  One thread per term; scalars are 32-byte canonical little-endian.
+__global__ void __launch_bounds__(256) k_msm_count(const uint8_t *__restrict__ scalars, const uint32_t *__restrict__ offsets, uint32_t n_msm, uint32_t T,
+                                                   int c, int W, uint32_t *__restrict__ counts, uint32_t *__restrict__ msm_err) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    uint8_t sb[32]; ld32(sb, scalars + 32 * (size_t)t);
+    sc s = sc_load(sb);
+    uint32_t msm = n_msm == 1 ? 0u : msm_of_term(offsets, n_msm, t);
+    if (sc_geq_l(s)) { if (msm_err) atomicOr(msm_err + msm, 2u); return; }       // non-canonical scalar
+    msm_wide r = msm_recode(s.v, c, W);
+    uint32_t nb = 1u << (c - 1);
+    for (int w = 0; w < W; w++) {
+        int d = msm_digit(r, w, c);
+        if (d == 0) continue;
+        uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
+        atomicAdd(counts + ((size_t)msm * W + w) * nb + b, 1u);
+    }
+}
+// pass 2: per-segment exclusive scan of the bucket counts (block per segment); cursor starts as a copy
+__global__ void __launch_bounds__(256) k_msm_scan(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t *__restrict__ starts, uint32_t *__restrict__ cursor) {
+    __shared__ uint32_t warp_sums[8];
+    size_t seg = blockIdx.x;
+    const uint32_t *cnt = counts + seg * nb; uint32_t *st = starts + seg * nb, *cu = cursor + seg * nb;
+    uint32_t per = (nb + blockDim.x - 1) / blockDim.x;
+    uint32_t lo = threadIdx.x * per, hi = min(lo + per, nb);
+    uint32_t local = 0;
+    for (uint32_t i = lo; i < hi; i++) local += cnt[i];
+    // block exclusive scan of `local`
+    uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5, v = local;
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, v, d); if (lane >= (uint32_t)d) v += o; }
+    if (lane == 31) warp_sums[wid] = v;
+    __syncthreads();
+    uint32_t base = 0;
+    for (uint32_t k = 0; k < wid; k++) base += warp_sums[k];
+    uint32_t run = base + v - local;
+    for (uint32_t i = lo; i < hi; i++) { st[i] = run; cu[i] = run; run += cnt[i]; }
+}
+// pass 3: scatter term ids (sign in bit 31) into their bucket's slice
+__global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *__restrict__ scalars, const uint32_t *__restrict__ offsets, uint32_t n_msm, uint32_t T,
+                                                     int c, int W, uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    uint8_t sb[32]; ld32(sb, scalars + 32 * (size_t)t);
+    sc s = sc_load(sb);
+    if (sc_geq_l(s)) return;
+    uint32_t msm = n_msm == 1 ? 0u : msm_of_term(offsets, n_msm, t);
+    uint32_t o0 = __ldg(offsets + msm), len = __ldg(offsets + msm + 1) - o0;
+    msm_wide r = msm_recode(s.v, c, W);
+    uint32_t nb = 1u << (c - 1);
+    for (int w = 0; w < W; w++) {
+        int d = msm_digit(r, w, c);
+        if (d == 0) continue;
+        uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
+        uint32_t pos = atomicAdd(cursor + ((size_t)msm * W + w) * nb + b, 1u);
+        sorted[(size_t)W * o0 + (size_t)w * len + pos] = t | (d < 0 ? 0x80000000u : 0u);
+    }
+}
+// pass 4: bucket accumulation, one thread per bucket: sum of +-points listed in its slice (mixed additions)
+__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
+                                                        const uint32_t *__restrict__ offsets, int W, uint32_t nb, size_t n_buckets,
+                                                        const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,
+                                                        ge_ext *__restrict__ buckets) {
+    size_t gb = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gb >= n_buckets) return;
+    size_t seg = gb / nb; uint32_t msm = (uint32_t)(seg / W), w = (uint32_t)(seg % W);
+    uint32_t o0 = __ldg(offsets + msm), len = __ldg(offsets + msm + 1) - o0;
+    const uint32_t *slice = sorted + (size_t)W * o0 + (size_t)w * len;
+    uint32_t lo = starts[gb], hi = ends[gb];
+    ge_ext acc = ge_identity();
+    for (uint32_t e = lo; e < hi; e++) {
+        uint32_t v = __ldg(slice + e), t = v & 0x7fffffffu;
+        uint32_t pi = point_idx ? __ldg(point_idx + t) : (t | BP_POINT_DYNAMIC);
+        const ge_niels *src = (pi & BP_POINT_DYNAMIC) ? pts_dynamic + (pi & 0x7fffffffu) : pts_static + pi;
+        ge_niels q = ldg_niels(src);
+        if (v & 0x80000000u) q = ge_niels_neg(q);
+        acc = ge_madd(acc, q);
+    }
+    st_ext(buckets + gb, acc);
+}
+// pass 5: bucket reduction  R = sum_j (j+1) B_j  per segment, one block per segment.
+// Each thread owns a contiguous chunk; a warp-shuffle suffix scan over the chunk sums gives every
+// thread the sum of all buckets above its chunk, then one running-sum pass finishes the chunk and
+// a shuffle tree adds the per-thread results.
+__global__ void __launch_bounds__(256) k_msm_reduce(const ge_ext *__restrict__ buckets, uint32_t nb, ge_ext *__restrict__ window_sums) {
+    __shared__ ge_ext sm[8];
+    size_t seg = blockIdx.x;
+    const ge_ext *B = buckets + seg * nb;
+    uint32_t nthreads = blockDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarps = nthreads >> 5;
+    uint32_t L = (nb + nthreads - 1) / nthreads;
+    uint32_t lo = min(tid * L, nb), hi = min(lo + L, nb);
+    // 1. chunk sum
+    ge_ext S = ge_identity();
+    for (uint32_t j = lo; j < hi; j++) S = ge_add(S, ld_ext(B + j));
+    // 2. inclusive suffix scan across the block
+    ge_ext suf = S;
+#pragma unroll 1
+    for (int d = 1; d < 32; d <<= 1) { ge_ext o = shfl_down_ext(suf, d); if (lane + d < 32) suf = ge_add(suf, o); }
+    if (lane == 0) sm[wid] = suf;               // total of this warp
+    __syncthreads();
+    ge_ext above = ge_identity();               // total of the warps holding higher buckets
+#pragma unroll 1
+    for (uint32_t k = wid + 1; k < nwarps; k++) above = ge_add(above, sm[k]);
+    // exclusive suffix: everything strictly above this thread's chunk
+    ge_ext next = shfl_down_ext(suf, 1);
+    ge_ext run = lane == 31 ? above : ge_add(next, above);
+    // 3. running-sum pass over the chunk, top bucket first
+    ge_ext acc = ge_identity();
+    for (uint32_t j = hi; j > lo; j--) { run = ge_add(run, ld_ext(B + j - 1)); acc = ge_add(acc, run); }
+    // 4. block sum of acc
+#pragma unroll 1
+    for (int d = 16; d >= 1; d >>= 1) { ge_ext o = shfl_down_ext(acc, d); acc = ge_add(acc, o); }
+    __syncthreads();
+    if (lane == 0) sm[wid] = acc;
+    __syncthreads();
+    if (tid == 0) { ge_ext r = sm[0]; for (uint32_t k = 1; k < nwarps; k++) r = ge_add(r, sm[k]); st_ext(window_sums + seg, r); }
+}
+// pass 6: window combination (Horner with c doublings per window), one thread per MSM
+__global__ void k_msm_combine(const ge_ext *__restrict__ window_sums, uint32_t n_msm, int c, int W, ge_ext *__restrict__ results) {
+    uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_msm) return;
+    const ge_ext *R = window_sums + (size_t)m * W;
+    ge_ext acc = ld_ext(R + W - 1);
+#pragma unroll 1
+    for (int w = W - 2; w >= 0; w--) {
+#pragma unroll 1
+        for (int i = 0; i < c; i++) acc = ge_dbl(acc);
+        acc = ge_add(acc, ld_ext(R + w));
+    }
+    st_ext(results + m, acc);
+}
+
+// ------------------------------------------------------------------ range-proof batch verification kernels
+struct rp_geom { uint32_t n, m, k, N, D, S; uint32_t proof_len; };   // D = 4+2k+m dynamic terms, S = 2+2N static terms
+
+// K5/K6: per-proof transcript replay + verification scalars.  One block per proof.
+//   contrib : count x S Montgomery scalars (rho-weighted static-term scalars: B~, B, G.., H..)
+//   dyn     : count x D canonical scalars, written straight into the MSM scalar array
+__global__ void __launch_bounds__(128) k_rp_prep(const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ commitments, rp_geom g,
+                                                 const uint8_t *__restrict__ tstate, const uint8_t *__restrict__ seed, uint32_t count,
+                                                 sc *__restrict__ contrib, uint8_t *__restrict__ dyn_scalars, uint32_t *__restrict__ status) {
+    __shared__ rp_head h;
+    uint32_t p = blockIdx.x;
+    if (p >= count) return;
+    const uint8_t *proof = proofs + (size_t)p * g.proof_len, *V = commitments + (size_t)p * g.m * 32;
+    if (threadIdx.x == 0) {
+        // per-proof batching weights: Keccak-f PRF keyed by the 32-byte seed, domain-separated by the proof index
+        uint64_t st[25];
+        for (int i = 0; i < 25; i++) st[i] = 0;
+        for (int i = 0; i < 4; i++) { uint64_t wv = 0; for (int j = 0; j < 8; j++) wv |= (uint64_t)seed[8 * i + j] << (8 * j); st[i] = wv; }
+        st[4] = p; st[5] = 0x62702d7765696768ULL;  /* "bp-weigh" */ st[16] ^= 0x8000000000000000ULL;
+        keccak_f1600(st);
+        uint8_t weights[128];
+        for (int i = 0; i < 16; i++) for (int j = 0; j < 8; j++) weights[8 * i + j] = (uint8_t)(st[i] >> (8 * j));
+        rp_prep_head(h, proof, g.k, V, g.n, g.m, tstate, weights);
+        status[p] = h.status;
+    }
+    __syncthreads();
+    sc *my = contrib + (size_t)p * g.S;
+    uint8_t *dyn = dyn_scalars + (size_t)p * g.D * 32;
+    if (h.status != BP_PROOF_OK) {            // malformed proof: contributes nothing to the combination
+        for (uint32_t i = threadIdx.x; i < g.S; i += blockDim.x) my[i] = sc_zero();
+        for (uint32_t i = threadIdx.x; i < g.D * 8; i += blockDim.x) reinterpret_cast<uint32_t *>(dyn)[i] = 0;
+        return;
+    }
+    if (threadIdx.x == 0) { my[0] = h.blinding_scalar; my[1] = h.basepoint_scalar; }
+    for (uint32_t i = threadIdx.x; i < g.N; i += blockDim.x) {
+        sc gi, hi; rp_prep_gh(h, i, g.k, g.n, gi, hi);
+        my[2 + i] = gi; my[2 + g.N + i] = hi;
+    }
+    for (uint32_t i = threadIdx.x; i < g.D; i += blockDim.x) {
+        sc v = sc_from_mont(rp_prep_dynamic(h, i, g.k));
+        uint8_t b[32]; sc_store(b, v); st32(dyn + 32 * i, b);
+    }
+}
+// decompress the per-proof points in MSM order A,S,T_1,T_2,L..,R..,V.. straight out of the proof bytes
+__global__ void __launch_bounds__(128) k_rp_decompress(const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ commitments, rp_geom g, uint32_t count,
+                                                       ge_niels *__restrict__ out, uint32_t *__restrict__ status) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)count * g.D) return;
+    uint32_t p = (uint32_t)(i / g.D), idx = (uint32_t)(i % g.D);
+    const uint8_t *proof = proofs + (size_t)p * g.proof_len, *src;
+    if (idx < 4) src = proof + 32 * idx;
+    else if (idx < 4 + g.k) src = proof + 224 + 64 * (idx - 4);
+    else if (idx < 4 + 2 * g.k) src = proof + 224 + 64 * (idx - 4 - g.k) + 32;
+    else src = commitments + ((size_t)p * g.m + (idx - 4 - 2 * g.k)) * 32;
+    uint8_t s[32]; ld32_any(s, src);
+    fe x, y; bool valid = ge_decode(x, y, s);
+    st_niels(out + i, valid ? ge_to_niels_affine(x, y) : ge_niels_identity());
+    if (!valid) atomicCAS(status + p, (uint32_t)BP_PROOF_OK, (uint32_t)BP_PROOF_VERIFICATION_ERROR);
+}
+// sum the weighted static-term scalars over the proofs of the batch: one block per static term
+__global__ void __launch_bounds__(128) k_rp_static_reduce(const sc *__restrict__ contrib, uint32_t S, uint32_t count, uint8_t *__restrict__ out_scalars) {
+    __shared__ sc sm[4];
+    uint32_t s = blockIdx.x;
+    sc acc = sc_zero();
+    for (uint32_t p = threadIdx.x; p < count; p += blockDim.x) acc = sc_add(acc, contrib[(size_t)p * S + s]);
+    for (int d = 16; d >= 1; d >>= 1) {
+        sc o; for (int i = 0; i < 8; i++) o.v[i] = __shfl_down_sync(0xffffffffu, acc.v[i], d);
+        acc = sc_add(acc, o);
+    }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (uint32_t k = 1; k < (blockDim.x >> 5); k++) acc = sc_add(acc, sm[k]);
+        uint8_t b[32]; sc_store(b, sc_from_mont(acc)); st32(out_scalars + 32 * (size_t)s, b);
+    }
+}
+// fallback: expand contrib (Montgomery) into per-proof canonical scalar rows [S static | D dynamic]
+__global__ void k_rp_expand_scalars(const sc *__restrict__ contrib, const uint8_t *__restrict__ dyn_scalars, rp_geom g, uint32_t count, uint8_t *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t row = g.S + g.D;
+    if (i >= (size_t)count * row) return;
+    uint32_t p = (uint32_t)(i / row), t = (uint32_t)(i % row);
+    uint8_t b[32];
+    if (t < g.S) sc_store(b, sc_from_mont(contrib[(size_t)p * g.S + t]));
+    else ld32(b, dyn_scalars + ((size_t)p * g.D + (t - g.S)) * 32);
+    st32(out + 32 * i, b);
+}
+// final verdicts.  mode 0 (combined check): every proof with status OK inherits the batch result
+// flags[0]; mode 1 (per-proof check): flags[p].
+__global__ void k_rp_verdict(const uint32_t *__restrict__ status, const uint32_t *__restrict__ flags, int per_proof, uint32_t count,
+                             uint32_t *__restrict__ verdict, uint32_t *__restrict__ batch_ok) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= count) return;
+    uint32_t st = status[p];
+    uint32_t ok = per_proof ? flags[p] : flags[0];
+    uint32_t v = st != BP_PROOF_OK ? st : (ok ? BP_PROOF_OK : BP_PROOF_VERIFICATION_ERROR);
+    verdict[p] = v;
+    if (!per_proof && v != BP_PROOF_OK) atomicExch(batch_ok, 0u);   // combined check failed or a proof was malformed
+}

@@ -1,0 +1,141 @@
+/* bpmsm.h — C ABI of the B200-native Ristretto255 multiscalar-multiplication engine.
+ *
+ * This is the drop-in boundary for the MSM-bound hot path of dalek-cryptography/bulletproofs.
+ * The reference has no FFI; its only seam is the Rust trait surface of curve25519_dalek::traits
+ * that the crate calls.  Each entry point below names the reference call site it replaces; the
+ * Rust-side binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Wire types:
+ *   scalar            32 bytes, little-endian, canonical (< l)          = curve25519_dalek::scalar::Scalar::as_bytes()
+ *   compressed point  32 bytes, canonical Ristretto255 encoding         = CompressedRistretto::as_bytes()
+ *   transcript        203 bytes: STROBE-128 state (200) ‖ pos ‖ pos_begin ‖ cur_flags  = merlin::Transcript fields
+ *
+ * Ownership: the caller owns every host buffer for the duration of the call; the library copies
+ * in and out and retains nothing except the explicit handles (bp_ctx, bp_gens).
+ * Threading: a bp_ctx is one device + one CUDA stream and is not thread-safe; different
+ * contexts may be used concurrently.  There is no hidden global state and no CPU fallback:
+ * every call fails with BP_ERR_CUDA when no sm_100 device is usable.
+ * Timing: all work is variable-time (like the reference's vartime_* calls).  The reference's
+ * constant-time `multiscalar_mul` sites (prover secrets) are served by the same variable-time
+ * kernels; see DESIGN.md "constant-time policy".
+ */
+#ifndef BPMSM_H
+#define BPMSM_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* call status */
+#define BP_OK 0
+#define BP_ERR_INVALID_POINT 1        /* a point failed to decompress: optional_multiscalar_mul -> None (range_proof/mod.rs:445) */
+#define BP_ERR_LENGTH_MISMATCH 2      /* the reference panics (assert_eq!, inner_product_proof.rs:59-67) */
+#define BP_ERR_NONCANONICAL_SCALAR 3  /* scalar bytes >= l: Scalar::from_canonical_bytes -> None */
+#define BP_ERR_CUDA 4                 /* no device / launch failure; bp_last_error() has the text */
+#define BP_ERR_INVALID_ARGUMENT 5
+
+/* per-proof verdicts = ProofError variants (/root/reference/src/errors.rs:12-54) */
+#define BP_PROOF_OK 0
+#define BP_PROOF_VERIFICATION_ERROR 1
+#define BP_PROOF_FORMAT_ERROR 2
+#define BP_PROOF_INVALID_BITSIZE 3
+#define BP_PROOF_INVALID_GENERATORS_LENGTH 4
+#define BP_PROOF_INVALID_AGGREGATION 5
+
+#define BP_TRANSCRIPT_BYTES 203
+
+typedef struct bp_ctx bp_ctx;
+typedef struct bp_gens bp_gens;
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* stream: a cudaStream_t to run on (e.g. torch.cuda.current_stream().cuda_stream), or NULL to
+ * create a private non-blocking stream. */
+int bp_ctx_create(int device, void *stream, bp_ctx **out);
+void bp_ctx_destroy(bp_ctx *ctx);
+const char *bp_last_error(const bp_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t bp_ctx_launch_count(const bp_ctx *ctx);
+/* block until all work queued on the context's stream is finished */
+int bp_ctx_synchronize(bp_ctx *ctx);
+
+/* ---- group primitives ---------------------------------------------------------------------- */
+/* CompressedRistretto::decompress for n points: ok[i] = 1 if point i is a valid encoding.
+ * Replaces the inline decompress() calls of range_proof/mod.rs:433-443. */
+int bp_decompress_check_batch(bp_ctx *ctx, const uint8_t *points, size_t n, uint8_t *ok);
+/* RistrettoPoint::from_uniform_bytes (generators.rs:94-99) for n 64-byte inputs -> n compressed points */
+int bp_from_uniform_bytes_batch(bp_ctx *ctx, const uint8_t *uniform, size_t n, uint8_t *points_out);
+
+/* ---- multiscalar multiplication ------------------------------------------------------------ */
+/* RistrettoPoint::vartime_multiscalar_mul / optional_multiscalar_mul on wire types:
+ *   out = compress( sum_i scalars[i] * decompress(points[i]) ).
+ * Call sites replaced: inner_product_proof.rs:87,101,127,131,153,159,177,178,308;
+ * range_proof/mod.rs:421; range_proof/messages.rs:128,149; generators.rs:40; range_proof/party.rs:119.
+ * Returns BP_ERR_INVALID_POINT if any point does not decode (the reference's `None`). */
+int bp_msm(bp_ctx *ctx, const uint8_t *scalars, const uint8_t *points, size_t n, uint8_t out[32]);
+/* n_msm independent MSMs in one launch sequence: MSM j uses terms offsets[j] .. offsets[j+1]-1.
+ * outs = n_msm x 32 bytes; status[j] = BP_OK / BP_ERR_INVALID_POINT / BP_ERR_NONCANONICAL_SCALAR. */
+int bp_msm_batch(bp_ctx *ctx, const uint8_t *scalars, const uint8_t *points, const uint64_t *offsets,
+                 size_t n_msm, uint8_t *outs, uint8_t *status);
+/* Same with every array already resident in device memory (16-byte aligned device pointers);
+ * work is queued on the context's stream and the call returns without synchronising. */
+int bp_msm_batch_device(bp_ctx *ctx, const void *d_scalars, const void *d_points, const void *d_offsets_u32,
+                        size_t n_msm, size_t total_terms, void *d_outs, void *d_status);
+
+/* ---- generator tables ---------------------------------------------------------------------- */
+/* BulletproofGens::new(gens_capacity, party_capacity) + PedersenGens::default()
+ * (generators.rs:44-53,157-204): SHAKE256 expansion on the host, Elligator maps and the
+ * table (affine Niels form, 96 B/point) on the device, where it stays resident. */
+int bp_gens_create(bp_ctx *ctx, size_t gens_capacity, size_t party_capacity, bp_gens **out);
+void bp_gens_destroy(bp_gens *gens);
+/* compressed generator: which = 0 -> G, 1 -> H (party, index); 2 -> B; 3 -> B_blinding */
+int bp_gens_get(bp_gens *gens, int which, size_t party, size_t index, uint8_t out[32]);
+/* device pointer + size of the resident table, layout [B_blinding, B, G[party][i]..., H[party][i]...]:
+ * this is the buffer broadcast once over NCCL at start-up. */
+int bp_gens_device_table(bp_gens *gens, void **d_table, size_t *bytes);
+/* an uninitialised table of the same geometry, to be filled by a broadcast from rank 0 */
+int bp_gens_create_empty(bp_ctx *ctx, size_t gens_capacity, size_t party_capacity, bp_gens **out);
+
+/* ---- range proofs -------------------------------------------------------------------------- */
+/* Batch verifier: `count` proofs with the same (n, m), each proof_len =
+ * 32*(9 + 2*lg(n*m)) bytes as written by RangeProof::to_bytes (range_proof/mod.rs:487-499), each
+ * with m commitments.  Every proof is checked exactly as RangeProof::verify_multiple
+ * (range_proof/mod.rs:345-452) would: verdict[i] = BP_PROOF_OK iff the reference returns Ok(()).
+ * All proofs start from the same transcript state.  Internally one random-linear-combination
+ * MSM covers the whole batch; if it does not vanish, every proof is re-checked on its own.
+ * seed: 32 bytes of randomness for the batching weights (the reference's `Scalar::random(rng)`,
+ * mod.rs:396), or NULL to draw from the OS. */
+int bp_rangeproof_verify_batch(bp_ctx *ctx, bp_gens *gens, const uint8_t transcript[BP_TRANSCRIPT_BYTES],
+                               const uint8_t *proofs, size_t proof_len, const uint8_t *commitments,
+                               size_t n, size_t m, size_t count, const uint8_t seed[32], uint8_t *verdicts);
+/* Asynchronous form for pipelining host buffers (pinned memory recommended): queues the H2D copies,
+ * all kernels and the D2H copy of the verdicts on the context's stream; call
+ * bp_rangeproof_verify_finish() to synchronise and run the rare per-proof fallback. */
+int bp_rangeproof_verify_begin(bp_ctx *ctx, bp_gens *gens, const uint8_t transcript[BP_TRANSCRIPT_BYTES],
+                               const uint8_t *proofs, size_t proof_len, const uint8_t *commitments,
+                               size_t n, size_t m, size_t count, const uint8_t seed[32]);
+int bp_rangeproof_verify_finish(bp_ctx *ctx, uint8_t *verdicts);
+/* Device-resident form: proofs/commitments are device pointers; verdicts stay on the device
+ * (count x uint32).  Used for the HBM-resident throughput measurement. */
+int bp_rangeproof_verify_batch_device(bp_ctx *ctx, bp_gens *gens, const uint8_t transcript[BP_TRANSCRIPT_BYTES],
+                                      const void *d_proofs, size_t proof_len, const void *d_commitments,
+                                      size_t n, size_t m, size_t count, const uint8_t seed[32], void *d_verdicts_u32,
+                                      uint32_t *h_batch_ok_pinned);
+
+/* ---- host helpers -------------------------------------------------------------------------- */
+/* merlin::Transcript for callers without the Rust crate (same framing as transcript.rs:43-94 expects):
+ * Transcript::new(label), append_message, append_u64, challenge_bytes on the 203-byte wire state. */
+void bp_transcript_new(const uint8_t *label, size_t len, uint8_t out[BP_TRANSCRIPT_BYTES]);
+void bp_transcript_append_message(uint8_t state[BP_TRANSCRIPT_BYTES], const char *label, const uint8_t *msg, size_t len);
+void bp_transcript_append_u64(uint8_t state[BP_TRANSCRIPT_BYTES], const char *label, uint64_t x);
+void bp_transcript_challenge_bytes(uint8_t state[BP_TRANSCRIPT_BYTES], const char *label, uint8_t *out, size_t len);
+
+/* ---- test hook ----------------------------------------------------------------------------- */
+/* element-wise field operation on the device over n pairs of 32-byte little-endian values:
+ * op 0 add, 1 sub, 2 mul, 3 invert(a), 4 a^((p-5)/8), 5 neg(a), 6 a^2, 7 (a+b)(a-b); canonical bytes out */
+int bp_debug_fe_op(bp_ctx *ctx, int op, const uint8_t *a, const uint8_t *b, size_t n, uint8_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

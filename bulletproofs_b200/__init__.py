@@ -38,6 +38,12 @@ SYMBOLS = {
     "bp_rangeproof_verify_begin": (_int, [_vp, _vp, _u8p, _vp, _sz, _vp, _sz, _sz, _sz, _u8p]),
     "bp_rangeproof_verify_finish": (_int, [_vp, _u8p]),
     "bp_rangeproof_verify_batch_device": (_int, [_vp, _vp, _u8p, _vp, _sz, _vp, _sz, _sz, _sz, _u8p, _vp, _vp]),
+    "bp_gens_table_export": (_int, [_vp, _vp]),
+    "bp_gens_table_import": (_int, [_vp, _vp]),
+    "bp_prof_enable": (_int, [_vp, _int]),
+    "bp_prof_kernel_count": (_int, []),
+    "bp_prof_kernel_name": (_c.c_char_p, [_int]),
+    "bp_prof_report": (_int, [_vp, _c.POINTER(_c.c_double), _c.POINTER(_c.c_uint64)]),
     "bp_transcript_new": (None, [_u8p, _sz, _u8p]),
     "bp_transcript_append_message": (None, [_u8p, _u8p, _u8p, _sz]),
     "bp_transcript_append_u64": (None, [_u8p, _u8p, _c.c_uint64]),
@@ -129,6 +135,16 @@ class Context:
     def synchronize(self):
         self._check(lib().bp_ctx_synchronize(self._h))
 
+    def prof_enable(self, on=True):
+        self._check(lib().bp_prof_enable(self._h, 1 if on else 0))
+
+    def prof_report(self):
+        """{kernel name: (total ms, launches)} from CUDA events since the last report (synchronises)."""
+        n = lib().bp_prof_kernel_count()
+        ms, cnt = (ctypes.c_double * n)(), (ctypes.c_uint64 * n)()
+        self._check(lib().bp_prof_report(self._h, ms, cnt))
+        return {lib().bp_prof_kernel_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}
+
     # ---- group primitives
     def decompress_check(self, points: bytes):
         n = len(points) // 32
@@ -196,6 +212,12 @@ class Gens:
     def B_blinding(self):
         return self.get(3)
 
+    def table_export(self, d_dst: int):
+        self.ctx._check(lib().bp_gens_table_export(self._h, d_dst))
+
+    def table_import(self, d_src: int):
+        self.ctx._check(lib().bp_gens_table_import(self._h, d_src))
+
     def device_table(self):
         p, n = _vp(), _sz()
         self.ctx._check(lib().bp_gens_device_table(self._h, ctypes.byref(p), ctypes.byref(n)))
@@ -205,6 +227,34 @@ class Gens:
         if self._h:
             lib().bp_gens_destroy(self._h)
             self._h = _vp()
+
+
+class BatchVerifier:
+    """Pipelined form of the batch verifier over raw buffers (bench.py): `begin` queues the H2D copies, kernels
+    and the verdict D2H on the context's stream, `finish` synchronises and returns the verdict codes."""
+
+    def __init__(self, ctx: Context, gens: Gens, transcript: Transcript, n: int, m: int, count: int):
+        self.ctx, self.gens, self.n, self.m, self.count = ctx, gens, n, m, count
+        self.t = transcript.to_bytes()
+        self.proof_len = rangeproof_size(n, m)
+        self._verdicts = ctypes.create_string_buffer(count)
+        self.busy = False
+
+    def begin(self, proofs_ptr: int, commitments_ptr: int, seed: bytes = None):
+        """proofs_ptr / commitments_ptr: host addresses (pinned memory for truly asynchronous copies)."""
+        self.ctx._check(lib().bp_rangeproof_verify_begin(self.ctx._h, self.gens._h, self.t, proofs_ptr, self.proof_len, commitments_ptr,
+                                                         self.n, self.m, self.count, seed))
+        self.busy = True
+
+    def finish(self):
+        self.ctx._check(lib().bp_rangeproof_verify_finish(self.ctx._h, self._verdicts))
+        self.busy = False
+        return self._verdicts.raw
+
+    def run_device(self, d_proofs: int, d_commitments: int, d_verdicts_u32: int, h_batch_ok_pinned: int = None, seed: bytes = None):
+        """device-resident inputs; nothing is synchronised (verdicts stay on the device)."""
+        self.ctx._check(lib().bp_rangeproof_verify_batch_device(self.ctx._h, self.gens._h, self.t, d_proofs, self.proof_len, d_commitments,
+                                                                self.n, self.m, self.count, seed, d_verdicts_u32, h_batch_ok_pinned))
 
 
 def rangeproof_size(n: int, m: int) -> int:

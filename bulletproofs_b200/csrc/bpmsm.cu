@@ -29,6 +29,12 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+enum KernelId { KID_DECOMPRESS, KID_COMPRESS, KID_FROM_UNIFORM, KID_MSM_COUNT, KID_MSM_SCAN, KID_MSM_SCATTER, KID_MSM_ACCUMULATE, KID_MSM_REDUCE,
+                KID_MSM_COMBINE, KID_RP_PREP, KID_RP_DECOMPRESS, KID_RP_STATIC_REDUCE, KID_SMALL, KID_COUNT };
+const char *const KERNEL_NAMES[KID_COUNT] = {"k_decompress", "k_compress", "k_from_uniform", "k_msm_count", "k_msm_scan", "k_msm_scatter", "k_msm_accumulate",
+                                             "k_msm_reduce", "k_msm_combine", "k_rp_prep", "k_rp_decompress", "k_rp_static_reduce", "small_kernels"};
+struct ProfRec { int kid; cudaEvent_t a, b; };
+
 struct VerifyState {          // what bp_rangeproof_verify_begin leaves for _finish
     bool active = false; rp_geom g{}; uint32_t count = 0; bp_gens *gens = nullptr;
     const uint8_t *d_proofs = nullptr, *d_commitments = nullptr;
@@ -39,6 +45,7 @@ struct VerifyState {          // what bp_rangeproof_verify_begin leaves for _fin
 struct bp_ctx {
     int device = 0; cudaStream_t stream = nullptr; bool own_stream = false;
     std::string err; uint64_t launches = 0;
+    bool prof_on = false; std::vector<ProfRec> prof;          // per-kernel CUDA-event timing (bp_prof_*)
     // MSM scratch
     DevBuf in_scalars, in_points, in_offsets, niels, ok, msm_err, counts, starts, cursor, sorted, buckets, wsums, results, outs, flags;
     // range-proof scratch
@@ -60,6 +67,16 @@ namespace {
     do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_); return BP_ERR_CUDA; } } while (0)
 #define LAUNCH_CHECK(ctx)                                                                              \
     do { (ctx)->launches++; cudaError_t e_ = cudaGetLastError(); if (e_ != cudaSuccess) { (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e_); return BP_ERR_CUDA; } } while (0)
+
+// launch wrapper: counts the launch and, when profiling is enabled, brackets it with CUDA events on the launching stream
+#define LAUNCH(ctx, kid, ...)                                                                          \
+    do {                                                                                               \
+        ProfRec pr_{(kid), nullptr, nullptr};                                                          \
+        if ((ctx)->prof_on) { cudaEventCreate(&pr_.a); cudaEventCreate(&pr_.b); cudaEventRecord(pr_.a, (ctx)->stream); } \
+        __VA_ARGS__;                                                                                   \
+        if ((ctx)->prof_on) { cudaEventRecord(pr_.b, (ctx)->stream); (ctx)->prof.push_back(pr_); }     \
+        LAUNCH_CHECK(ctx);                                                                             \
+    } while (0)
 
 inline unsigned blocks_for(size_t n, unsigned threads) { return (unsigned)((n + threads - 1) / threads); }
 
@@ -93,20 +110,14 @@ int msm_core(bp_ctx *ctx, const MsmArgs &a, ge_ext *d_results) {
     CK(ctx, ctx->sorted.ensure((size_t)a.T * W * 4)); CK(ctx, ctx->buckets.ensure(n_buckets * sizeof(ge_ext))); CK(ctx, ctx->wsums.ensure(segs * sizeof(ge_ext)));
     cudaStream_t s = ctx->stream;
     CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, n_buckets * 4, s));
-    k_msm_count<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->counts.as<uint32_t>(), a.d_err);
-    LAUNCH_CHECK(ctx);
-    k_msm_scan<<<(unsigned)segs, 256, 0, s>>>(ctx->counts.as<uint32_t>(), nb, ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>());
-    LAUNCH_CHECK(ctx);
-    k_msm_scatter<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>());
-    LAUNCH_CHECK(ctx);
-    k_msm_accumulate<<<blocks_for(n_buckets, 128), 128, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(), a.d_offsets, W, nb,
-                                                                n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>());
-    LAUNCH_CHECK(ctx);
+    LAUNCH(ctx, KID_MSM_COUNT, k_msm_count<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->counts.as<uint32_t>(), a.d_err));
+    LAUNCH(ctx, KID_MSM_SCAN, k_msm_scan<<<(unsigned)segs, 256, 0, s>>>(ctx->counts.as<uint32_t>(), nb, ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>()));
+    LAUNCH(ctx, KID_MSM_SCATTER, k_msm_scatter<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>()));
+    LAUNCH(ctx, KID_MSM_ACCUMULATE, k_msm_accumulate<<<blocks_for(n_buckets, 128), 128, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(), a.d_offsets, W, nb,
+                                                                n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>()));
     unsigned rthreads = nb >= 256 ? 256 : (nb < 32 ? 32 : nb);
-    k_msm_reduce<<<(unsigned)segs, rthreads, 0, s>>>(ctx->buckets.as<ge_ext>(), nb, ctx->wsums.as<ge_ext>());
-    LAUNCH_CHECK(ctx);
-    k_msm_combine<<<blocks_for(a.n_msm, 32), 32, 0, s>>>(ctx->wsums.as<ge_ext>(), a.n_msm, c, W, d_results);
-    LAUNCH_CHECK(ctx);
+    LAUNCH(ctx, KID_MSM_REDUCE, k_msm_reduce<<<(unsigned)segs, rthreads, 0, s>>>(ctx->buckets.as<ge_ext>(), nb, ctx->wsums.as<ge_ext>()));
+    LAUNCH(ctx, KID_MSM_COMBINE, k_msm_combine<<<blocks_for(a.n_msm, 32), 32, 0, s>>>(ctx->wsums.as<ge_ext>(), a.n_msm, c, W, d_results));
     return BP_OK;
 }
 
@@ -186,8 +197,7 @@ int bp_decompress_check_batch(bp_ctx *c, const uint8_t *points, size_t n, uint8_
     CK(c, cudaSetDevice(c->device));
     CK(c, c->in_points.ensure(n * 32)); CK(c, c->niels.ensure(n * sizeof(ge_niels))); CK(c, c->ok.ensure(n));
     CK(c, cudaMemcpyAsync(c->in_points.p, points, n * 32, cudaMemcpyHostToDevice, c->stream));
-    k_decompress<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, c->niels.as<ge_niels>(), c->ok.as<uint8_t>());
-    LAUNCH_CHECK(c);
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, c->niels.as<ge_niels>(), c->ok.as<uint8_t>()));
     CK(c, cudaMemcpyAsync(ok, c->ok.p, n, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return BP_OK;
@@ -199,8 +209,7 @@ int bp_from_uniform_bytes_batch(bp_ctx *c, const uint8_t *uniform, size_t n, uin
     CK(c, cudaSetDevice(c->device));
     CK(c, c->in_points.ensure(n * 64)); CK(c, c->outs.ensure(n * 32));
     CK(c, cudaMemcpyAsync(c->in_points.p, uniform, n * 64, cudaMemcpyHostToDevice, c->stream));
-    k_from_uniform<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, nullptr, c->outs.as<uint8_t>());
-    LAUNCH_CHECK(c);
+    LAUNCH(c, KID_FROM_UNIFORM, k_from_uniform<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, nullptr, c->outs.as<uint8_t>()));
     CK(c, cudaMemcpyAsync(points_out, c->outs.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return BP_OK;
@@ -215,16 +224,13 @@ int bp_msm_batch_device(bp_ctx *c, const void *d_scalars, const void *d_points, 
     CK(c, c->niels.ensure((size_t)T * sizeof(ge_niels))); CK(c, c->ok.ensure(T)); CK(c, c->msm_err.ensure((size_t)M * 4)); CK(c, c->results.ensure((size_t)M * sizeof(ge_ext)));
     cudaStream_t s = c->stream;
     CK(c, cudaMemsetAsync(c->msm_err.p, 0, (size_t)M * 4, s));
-    k_decompress<<<blocks_for(T, 128), 128, 0, s>>>((const uint8_t *)d_points, T, c->niels.as<ge_niels>(), c->ok.as<uint8_t>());
-    LAUNCH_CHECK(c);
-    k_mark_invalid<<<blocks_for(T, 256), 256, 0, s>>>(c->ok.as<uint8_t>(), (const uint32_t *)d_offsets_u32, M, T, c->msm_err.as<uint32_t>());
-    LAUNCH_CHECK(c);
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(T, 128), 128, 0, s>>>((const uint8_t *)d_points, T, c->niels.as<ge_niels>(), c->ok.as<uint8_t>()));
+    LAUNCH(c, KID_SMALL, k_mark_invalid<<<blocks_for(T, 256), 256, 0, s>>>(c->ok.as<uint8_t>(), (const uint32_t *)d_offsets_u32, M, T, c->msm_err.as<uint32_t>()));
     MsmArgs a{(const uint8_t *)d_scalars, (const uint32_t *)d_offsets_u32, M, T, nullptr, nullptr, c->niels.as<ge_niels>(), c->msm_err.as<uint32_t>(), 0};
     int rc = msm_core(c, a, c->results.as<ge_ext>());
     if (rc) return rc;
-    k_compress<<<blocks_for(M, 128), 128, 0, s>>>(c->results.as<ge_ext>(), M, (uint8_t *)d_outs);
-    LAUNCH_CHECK(c);
-    if (d_status) { k_msm_status<<<blocks_for(M, 128), 128, 0, s>>>(c->msm_err.as<uint32_t>(), M, (uint8_t *)d_status); LAUNCH_CHECK(c); }
+    LAUNCH(c, KID_COMPRESS, k_compress<<<blocks_for(M, 128), 128, 0, s>>>(c->results.as<ge_ext>(), M, (uint8_t *)d_outs));
+    if (d_status) { LAUNCH(c, KID_SMALL, k_msm_status<<<blocks_for(M, 128), 128, 0, s>>>(c->msm_err.as<uint32_t>(), M, (uint8_t *)d_status)); }
     return BP_OK;
 }
 
@@ -297,10 +303,8 @@ int bp_gens_create(bp_ctx *c, size_t cap, size_t parties, bp_gens **out) {
     cudaStream_t s = c->stream;
     CK(c, cudaMemcpyAsync(c->in_points.p, uni.data(), uni.size(), cudaMemcpyHostToDevice, s));
     CK(c, cudaMemcpyAsync(c->in_scalars.p, BASEPOINT, 32, cudaMemcpyHostToDevice, s));
-    k_from_uniform<<<blocks_for(g->n_points, 128), 128, 0, s>>>(c->in_points.as<uint8_t>(), g->n_points, g->d_table, nullptr);
-    LAUNCH_CHECK(c);
-    k_decompress<<<1, 128, 0, s>>>(c->in_scalars.as<uint8_t>(), 1, g->d_table + 1, nullptr);
-    LAUNCH_CHECK(c);
+    LAUNCH(c, KID_FROM_UNIFORM, k_from_uniform<<<blocks_for(g->n_points, 128), 128, 0, s>>>(c->in_points.as<uint8_t>(), g->n_points, g->d_table, nullptr));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<1, 128, 0, s>>>(c->in_scalars.as<uint8_t>(), 1, g->d_table + 1, nullptr));
     CK(c, cudaStreamSynchronize(s));
     return BP_OK;
 }
@@ -316,8 +320,7 @@ int bp_gens_get(bp_gens *g, int which, size_t party, size_t index, uint8_t out[3
     else if ((which == 0 || which == 1) && party < g->parties && index < g->cap) slot = 2 + ((size_t)which * g->parties + party) * g->cap + index;
     else return BP_ERR_INVALID_ARGUMENT;
     CK(c, cudaSetDevice(c->device)); CK(c, c->outs.ensure(32));
-    k_niels_to_compressed<<<1, 32, 0, c->stream>>>(g->d_table + slot, 1, c->outs.as<uint8_t>());
-    LAUNCH_CHECK(c);
+    LAUNCH(c, KID_SMALL, k_niels_to_compressed<<<1, 32, 0, c->stream>>>(g->d_table + slot, 1, c->outs.as<uint8_t>()));
     CK(c, cudaMemcpyAsync(out, c->outs.p, 32, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return BP_OK;
@@ -370,22 +373,16 @@ static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t 
     CK(c, cudaMemcpyAsync(c->rp_batch_ok.p, stage + 336, 4, cudaMemcpyHostToDevice, s));
 
     uint8_t *d_scal = c->rp_scalars.as<uint8_t>();
-    k_rp_prep<<<count, 128, 0, s>>>(d_proofs, d_commit, g, c->rp_tstate.as<uint8_t>(), c->rp_seed.as<uint8_t>(), count, c->rp_contrib.as<sc>(),
-                                    d_scal + (size_t)g.S * 32, c->rp_status.as<uint32_t>());
-    LAUNCH_CHECK(c);
-    k_rp_decompress<<<blocks_for((size_t)count * g.D, 128), 128, 0, s>>>(d_proofs, d_commit, g, count, c->niels.as<ge_niels>(), c->rp_status.as<uint32_t>());
-    LAUNCH_CHECK(c);
-    k_rp_static_reduce<<<g.S, 128, 0, s>>>(c->rp_contrib.as<sc>(), g.S, count, d_scal);
-    LAUNCH_CHECK(c);
-    k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 0, c->rp_pidx.as<uint32_t>());
-    LAUNCH_CHECK(c);
+    LAUNCH(c, KID_RP_PREP, k_rp_prep<<<count, 128, 0, s>>>(d_proofs, d_commit, g, c->rp_tstate.as<uint8_t>(), c->rp_seed.as<uint8_t>(), count, c->rp_contrib.as<sc>(),
+                                    d_scal + (size_t)g.S * 32, c->rp_status.as<uint32_t>()));
+    LAUNCH(c, KID_RP_DECOMPRESS, k_rp_decompress<<<blocks_for((size_t)count * g.D, 128), 128, 0, s>>>(d_proofs, d_commit, g, count, c->niels.as<ge_niels>(), c->rp_status.as<uint32_t>()));
+    LAUNCH(c, KID_RP_STATIC_REDUCE, k_rp_static_reduce<<<g.S, 128, 0, s>>>(c->rp_contrib.as<sc>(), g.S, count, d_scal));
+    LAUNCH(c, KID_SMALL, k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 0, c->rp_pidx.as<uint32_t>()));
     MsmArgs a{d_scal, c->rp_offsets.as<uint32_t>(), 1, T, c->rp_pidx.as<uint32_t>(), gens->d_table, c->niels.as<ge_niels>(), nullptr, 0};
     int rc = msm_core(c, a, c->results.as<ge_ext>());
     if (rc) return rc;
-    k_is_identity<<<1, 32, 0, s>>>(c->results.as<ge_ext>(), 1, c->flags.as<uint32_t>());
-    LAUNCH_CHECK(c);
-    k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 0, count, d_verdict, c->rp_batch_ok.as<uint32_t>());
-    LAUNCH_CHECK(c);
+    LAUNCH(c, KID_SMALL, k_is_identity<<<1, 32, 0, s>>>(c->results.as<ge_ext>(), 1, c->flags.as<uint32_t>()));
+    LAUNCH(c, KID_SMALL, k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 0, count, d_verdict, c->rp_batch_ok.as<uint32_t>()));
     return BP_OK;
 }
 
@@ -396,19 +393,14 @@ static int rp_verify_fallback(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32
     if (T >= (1u << 31)) { c->err = "fallback batch too large"; return BP_ERR_INVALID_ARGUMENT; }
     CK(c, c->fb_scalars.ensure(T * 32)); CK(c, c->fb_pidx.ensure(T * 4)); CK(c, c->fb_offsets.ensure(((size_t)count + 1) * 4));
     CK(c, c->results.ensure((size_t)count * sizeof(ge_ext))); CK(c, c->flags.ensure((size_t)count * 4));
-    k_rp_expand_scalars<<<blocks_for(T, 128), 128, 0, s>>>(c->rp_contrib.as<sc>(), c->rp_scalars.as<uint8_t>() + (size_t)g.S * 32, g, count, c->fb_scalars.as<uint8_t>());
-    LAUNCH_CHECK(c);
-    k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 1, c->fb_pidx.as<uint32_t>());
-    LAUNCH_CHECK(c);
-    k_fill_offsets<<<blocks_for((size_t)count + 1, 256), 256, 0, s>>>(count, row, c->fb_offsets.as<uint32_t>());
-    LAUNCH_CHECK(c);
+    LAUNCH(c, KID_SMALL, k_rp_expand_scalars<<<blocks_for(T, 128), 128, 0, s>>>(c->rp_contrib.as<sc>(), c->rp_scalars.as<uint8_t>() + (size_t)g.S * 32, g, count, c->fb_scalars.as<uint8_t>()));
+    LAUNCH(c, KID_SMALL, k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 1, c->fb_pidx.as<uint32_t>()));
+    LAUNCH(c, KID_SMALL, k_fill_offsets<<<blocks_for((size_t)count + 1, 256), 256, 0, s>>>(count, row, c->fb_offsets.as<uint32_t>()));
     MsmArgs a{c->fb_scalars.as<uint8_t>(), c->fb_offsets.as<uint32_t>(), count, (uint32_t)T, c->fb_pidx.as<uint32_t>(), gens->d_table, c->niels.as<ge_niels>(), nullptr, 0};
     int rc = msm_core(c, a, c->results.as<ge_ext>());
     if (rc) return rc;
-    k_is_identity<<<blocks_for(count, 128), 128, 0, s>>>(c->results.as<ge_ext>(), count, c->flags.as<uint32_t>());
-    LAUNCH_CHECK(c);
-    k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 1, count, d_verdict, c->rp_batch_ok.as<uint32_t>());
-    LAUNCH_CHECK(c);
+    LAUNCH(c, KID_SMALL, k_is_identity<<<blocks_for(count, 128), 128, 0, s>>>(c->results.as<ge_ext>(), count, c->flags.as<uint32_t>()));
+    LAUNCH(c, KID_SMALL, k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 1, count, d_verdict, c->rp_batch_ok.as<uint32_t>()));
     return BP_OK;
 }
 
@@ -469,6 +461,35 @@ int bp_rangeproof_verify_batch_device(bp_ctx *c, bp_gens *gens, const uint8_t *t
     return BP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- per-kernel timing
+int bp_prof_enable(bp_ctx *c, int on) {
+    if (!c) return BP_ERR_INVALID_ARGUMENT;
+    for (ProfRec &r : c->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    c->prof.clear(); c->prof_on = on != 0; return BP_OK;
+}
+int bp_prof_kernel_count(void) { return KID_COUNT; }
+const char *bp_prof_kernel_name(int kid) { return kid >= 0 && kid < KID_COUNT ? KERNEL_NAMES[kid] : ""; }
+// synchronises the stream, adds up the CUDA-event durations recorded since the last report; ms/counts have bp_prof_kernel_count() entries
+int bp_prof_report(bp_ctx *c, double *ms, uint64_t *counts) {
+    if (!c || !ms || !counts) return BP_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device)); CK(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < KID_COUNT; i++) { ms[i] = 0; counts[i] = 0; }
+    for (ProfRec &r : c->prof) { float t = 0; if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.kid] += t; counts[r.kid]++; } cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    c->prof.clear();
+    return BP_OK;
+}
+// copy the resident generator table to / from another device buffer (e.g. a torch tensor used for the NCCL broadcast)
+int bp_gens_table_export(bp_gens *g, void *d_dst) {
+    if (!g || !d_dst) return BP_ERR_INVALID_ARGUMENT;
+    bp_ctx *c = g->ctx; CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpyAsync(d_dst, g->d_table, g->n_points * sizeof(ge_niels), cudaMemcpyDeviceToDevice, c->stream)); CK(c, cudaStreamSynchronize(c->stream)); return BP_OK;
+}
+int bp_gens_table_import(bp_gens *g, const void *d_src) {
+    if (!g || !d_src) return BP_ERR_INVALID_ARGUMENT;
+    bp_ctx *c = g->ctx; CK(c, cudaSetDevice(c->device));
+    CK(c, cudaMemcpyAsync(g->d_table, d_src, g->n_points * sizeof(ge_niels), cudaMemcpyDeviceToDevice, c->stream)); CK(c, cudaStreamSynchronize(c->stream)); return BP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- host helpers
 // merlin::Transcript for hosts that do not have the Rust crate (the Python harness, C++ callers):
 // same STROBE code the device kernels use, compiled for the host.  Pure byte shuffling, no curve math.
@@ -505,8 +526,7 @@ int bp_debug_fe_op(bp_ctx *c, int op, const uint8_t *a, const uint8_t *b, size_t
     CK(c, c->in_scalars.ensure(n * 32)); CK(c, c->in_points.ensure(n * 32)); CK(c, c->outs.ensure(n * 32));
     CK(c, cudaMemcpyAsync(c->in_scalars.p, a, n * 32, cudaMemcpyHostToDevice, c->stream));
     CK(c, cudaMemcpyAsync(c->in_points.p, b, n * 32, cudaMemcpyHostToDevice, c->stream));
-    k_debug_fe<<<blocks_for(n, 128), 128, 0, c->stream>>>(op, c->in_scalars.as<uint8_t>(), c->in_points.as<uint8_t>(), n, c->outs.as<uint8_t>());
-    LAUNCH_CHECK(c);
+    LAUNCH(c, KID_SMALL, k_debug_fe<<<blocks_for(n, 128), 128, 0, c->stream>>>(op, c->in_scalars.as<uint8_t>(), c->in_points.as<uint8_t>(), n, c->outs.as<uint8_t>()));
     CK(c, cudaMemcpyAsync(out, c->outs.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return BP_OK;

@@ -122,6 +122,17 @@ int bp_rangeproof_verify_batch_device(bp_ctx *ctx, bp_gens *gens, const uint8_t 
                                       size_t n, size_t m, size_t count, const uint8_t seed[32], void *d_verdicts_u32,
                                       uint32_t *h_batch_ok_pinned);
 
+/* D2D copy of the resident table to / from a caller-owned device buffer of bp_gens_device_table() bytes
+ * (the Python harness broadcasts a torch tensor with NCCL and imports it on the other ranks). */
+int bp_gens_table_export(bp_gens *gens, void *d_dst);
+int bp_gens_table_import(bp_gens *gens, const void *d_src);
+
+/* ---- per-kernel timing (CUDA events on the launching stream; used by bench.py's roofline block) ---- */
+int bp_prof_enable(bp_ctx *ctx, int on);
+int bp_prof_kernel_count(void);
+const char *bp_prof_kernel_name(int kernel_id);
+int bp_prof_report(bp_ctx *ctx, double *ms, uint64_t *counts);
+
 /* ---- host helpers -------------------------------------------------------------------------- */
 /* merlin::Transcript for callers without the Rust crate (same framing as transcript.rs:43-94 expects):
  * Transcript::new(label), append_message, append_u64, challenge_bytes on the 203-byte wire state. */

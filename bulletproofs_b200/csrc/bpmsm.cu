@@ -30,9 +30,9 @@ struct DevBuf {
 };
 
 enum KernelId { KID_DECOMPRESS, KID_COMPRESS, KID_FROM_UNIFORM, KID_MSM_COUNT, KID_MSM_SCAN, KID_MSM_SCATTER, KID_MSM_ACCUMULATE, KID_MSM_REDUCE,
-                KID_MSM_COMBINE, KID_RP_PREP, KID_RP_DECOMPRESS, KID_RP_STATIC_REDUCE, KID_SMALL, KID_COUNT };
+                KID_MSM_COMBINE, KID_RP_TRANSCRIPT, KID_RP_SCALARS, KID_RP_DECOMPRESS, KID_RP_STATIC_REDUCE, KID_SMALL, KID_COUNT };
 const char *const KERNEL_NAMES[KID_COUNT] = {"k_decompress", "k_compress", "k_from_uniform", "k_msm_count", "k_msm_scan", "k_msm_scatter", "k_msm_accumulate",
-                                             "k_msm_reduce", "k_msm_combine", "k_rp_prep", "k_rp_decompress", "k_rp_static_reduce", "small_kernels"};
+                                             "k_msm_reduce", "k_msm_combine", "k_rp_transcript", "k_rp_scalars", "k_rp_decompress", "k_rp_static_reduce", "small_kernels"};
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
 struct VerifyState {          // what bp_rangeproof_verify_begin leaves for _finish
@@ -49,7 +49,7 @@ struct bp_ctx {
     // MSM scratch
     DevBuf in_scalars, in_points, in_offsets, niels, ok, msm_err, counts, starts, cursor, sorted, buckets, wsums, results, outs, flags;
     // range-proof scratch
-    DevBuf rp_proofs, rp_commit, rp_tstate, rp_seed, rp_contrib, rp_scalars, rp_status, rp_pidx, rp_offsets, rp_verdict, rp_batch_ok;
+    DevBuf rp_chal, rp_proofs, rp_commit, rp_tstate, rp_seed, rp_contrib, rp_scalars, rp_status, rp_pidx, rp_offsets, rp_verdict, rp_batch_ok;
     DevBuf fb_scalars, fb_pidx, fb_offsets;
     uint32_t *h_verdict = nullptr; size_t h_verdict_cap = 0;       // pinned
     uint32_t *h_flag = nullptr;                                      // pinned, 4 words
@@ -179,7 +179,7 @@ void bp_ctx_destroy(bp_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->in_scalars, &c->in_points, &c->in_offsets, &c->niels, &c->ok, &c->msm_err, &c->counts, &c->starts, &c->cursor, &c->sorted, &c->buckets,
-                      &c->wsums, &c->results, &c->outs, &c->flags, &c->rp_proofs, &c->rp_commit, &c->rp_tstate, &c->rp_seed, &c->rp_contrib, &c->rp_scalars,
+                      &c->wsums, &c->results, &c->outs, &c->flags, &c->rp_chal, &c->rp_proofs, &c->rp_commit, &c->rp_tstate, &c->rp_seed, &c->rp_contrib, &c->rp_scalars,
                       &c->rp_status, &c->rp_pidx, &c->rp_offsets, &c->rp_verdict, &c->rp_batch_ok, &c->fb_scalars, &c->fb_pidx, &c->fb_offsets};
     for (DevBuf *b : bufs) b->release();
     if (c->h_verdict) cudaFreeHost(c->h_verdict);
@@ -373,8 +373,10 @@ static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t 
     CK(c, cudaMemcpyAsync(c->rp_batch_ok.p, stage + 336, 4, cudaMemcpyHostToDevice, s));
 
     uint8_t *d_scal = c->rp_scalars.as<uint8_t>();
-    LAUNCH(c, KID_RP_PREP, k_rp_prep<<<count, 128, 0, s>>>(d_proofs, d_commit, g, c->rp_tstate.as<uint8_t>(), c->rp_seed.as<uint8_t>(), count, c->rp_contrib.as<sc>(),
-                                    d_scal + (size_t)g.S * 32, c->rp_status.as<uint32_t>()));
+    CK(c, c->rp_chal.ensure((size_t)count * sizeof(rp_head)));
+    LAUNCH(c, KID_RP_TRANSCRIPT, k_rp_transcript<<<blocks_for(count, RP_TR_THREADS), RP_TR_THREADS, 0, s>>>(d_proofs, d_commit, g, c->rp_tstate.as<uint8_t>(), c->rp_seed.as<uint8_t>(), count,
+                                                                                                           c->rp_chal.as<rp_head>(), c->rp_status.as<uint32_t>()));
+    LAUNCH(c, KID_RP_SCALARS, k_rp_scalars<<<blocks_for((size_t)count * (g.N + g.D), 128), 128, 0, s>>>(g, c->rp_chal.as<rp_head>(), count, c->rp_contrib.as<sc>(), d_scal + (size_t)g.S * 32));
     LAUNCH(c, KID_RP_DECOMPRESS, k_rp_decompress<<<blocks_for((size_t)count * g.D, 128), 128, 0, s>>>(d_proofs, d_commit, g, count, c->niels.as<ge_niels>(), c->rp_status.as<uint32_t>()));
     LAUNCH(c, KID_RP_STATIC_REDUCE, k_rp_static_reduce<<<g.S, 128, 0, s>>>(c->rp_contrib.as<sc>(), g.S, count, d_scal));
     LAUNCH(c, KID_SMALL, k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 0, c->rp_pidx.as<uint32_t>()));
@@ -493,13 +495,13 @@ int bp_gens_table_import(bp_gens *g, const void *d_src) {
 // ---------------------------------------------------------------------------------------------- host helpers
 // merlin::Transcript for hosts that do not have the Rust crate (the Python harness, C++ callers):
 // same STROBE code the device kernels use, compiled for the host.  Pure byte shuffling, no curve math.
-void bp_transcript_new(const uint8_t *label, size_t len, uint8_t out[BP_TRANSCRIPT_BYTES]) { merlin_t m; merlin_init(m, label, (uint32_t)len); merlin_store(out, m); }
+void bp_transcript_new(const uint8_t *label, size_t len, uint8_t out[BP_TRANSCRIPT_BYTES]) { alignas(8) uint8_t st[200]; merlin_t m; m.st = st; merlin_init(m, label, (uint32_t)len); merlin_store(out, m); }
 void bp_transcript_append_message(uint8_t state[BP_TRANSCRIPT_BYTES], const char *label, const uint8_t *msg, size_t len) {
-    merlin_t m; merlin_load(m, state); merlin_append(m, label, msg, (uint32_t)len); merlin_store(state, m);
+    alignas(8) uint8_t st[200]; merlin_t m; m.st = st; merlin_load(m, state); merlin_append(m, label, msg, (uint32_t)len); merlin_store(state, m);
 }
-void bp_transcript_append_u64(uint8_t state[BP_TRANSCRIPT_BYTES], const char *label, uint64_t x) { merlin_t m; merlin_load(m, state); merlin_append_u64(m, label, x); merlin_store(state, m); }
+void bp_transcript_append_u64(uint8_t state[BP_TRANSCRIPT_BYTES], const char *label, uint64_t x) { alignas(8) uint8_t st[200]; merlin_t m; m.st = st; merlin_load(m, state); merlin_append_u64(m, label, x); merlin_store(state, m); }
 void bp_transcript_challenge_bytes(uint8_t state[BP_TRANSCRIPT_BYTES], const char *label, uint8_t *out, size_t len) {
-    merlin_t m; merlin_load(m, state); merlin_challenge(m, label, out, (uint32_t)len); merlin_store(state, m);
+    alignas(8) uint8_t st[200]; merlin_t m; m.st = st; merlin_load(m, state); merlin_challenge(m, label, out, (uint32_t)len); merlin_store(state, m);
 }
 
 // test hook: element-wise field operation on the device (pins the PTX carry chains of fe.cuh)

@@ -247,44 +247,54 @@ __global__ void k_msm_combine(const ge_ext *__restrict__ window_sums, uint32_t n
 // ------------------------------------------------------------------ range-proof batch verification kernels
 struct rp_geom { uint32_t n, m, k, N, D, S; uint32_t proof_len; };   // D = 4+2k+m dynamic terms, S = 2+2N static terms
 
-// K5/K6: per-proof transcript replay + verification scalars.  One block per proof.
-//   contrib : count x S Montgomery scalars (rho-weighted static-term scalars: B~, B, G.., H..)
-//   dyn     : count x D canonical scalars, written straight into the MSM scalar array
-__global__ void __launch_bounds__(128) k_rp_prep(const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ commitments, rp_geom g,
-                                                 const uint8_t *__restrict__ tstate, const uint8_t *__restrict__ seed, uint32_t count,
-                                                 sc *__restrict__ contrib, uint8_t *__restrict__ dyn_scalars, uint32_t *__restrict__ status) {
-    __shared__ rp_head h;
-    uint32_t p = blockIdx.x;
+// K6: transcript replay + the sequential head of the scalar assembly.  One thread per proof (32 proofs
+// per warp, identical control flow, every lane busy); the STROBE state of each thread is a padded
+// shared-memory row (stride 204 B: conflict-free byte access).  Writes one rp_head per proof.
+#define RP_TR_THREADS 32
+__global__ void __launch_bounds__(RP_TR_THREADS) k_rp_transcript(const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ commitments, rp_geom g,
+                                                                   const uint8_t *__restrict__ tstate, const uint8_t *__restrict__ seed, uint32_t count,
+                                                                   rp_head *__restrict__ heads, uint32_t *__restrict__ status) {
+    __shared__ __align__(16) uint8_t rows[RP_TR_THREADS][204];
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= count) return;
     const uint8_t *proof = proofs + (size_t)p * g.proof_len, *V = commitments + (size_t)p * g.m * 32;
-    if (threadIdx.x == 0) {
-        // per-proof batching weights: Keccak-f PRF keyed by the 32-byte seed, domain-separated by the proof index
-        uint64_t st[25];
-        for (int i = 0; i < 25; i++) st[i] = 0;
-        for (int i = 0; i < 4; i++) { uint64_t wv = 0; for (int j = 0; j < 8; j++) wv |= (uint64_t)seed[8 * i + j] << (8 * j); st[i] = wv; }
-        st[4] = p; st[5] = 0x62702d7765696768ULL;  /* "bp-weigh" */ st[16] ^= 0x8000000000000000ULL;
-        keccak_f1600(st);
-        uint8_t weights[128];
-        for (int i = 0; i < 16; i++) for (int j = 0; j < 8; j++) weights[8 * i + j] = (uint8_t)(st[i] >> (8 * j));
-        rp_prep_head(h, proof, g.k, V, g.n, g.m, tstate, weights);
-        status[p] = h.status;
-    }
-    __syncthreads();
+    // per-proof batching weights: Keccak-f PRF keyed by the 32-byte seed, domain-separated by the proof index
+    uint64_t st[25];
+    for (int i = 0; i < 25; i++) st[i] = 0;
+    for (int i = 0; i < 4; i++) { uint64_t wv = 0; for (int j = 0; j < 8; j++) wv |= (uint64_t)seed[8 * i + j] << (8 * j); st[i] = wv; }
+    st[4] = p; st[5] = 0x62702d7765696768ULL;  /* "bp-weigh" */ st[16] ^= 0x8000000000000000ULL;
+    keccak_f1600(st);
+    uint8_t weights[128];
+    for (int i = 0; i < 16; i++) for (int j = 0; j < 8; j++) weights[8 * i + j] = (uint8_t)(st[i] >> (8 * j));
+    rp_challenges ch;
+    rp_transcript(ch, proof, g.k, V, g.n, g.m, tstate, weights, rows[threadIdx.x]);
+    status[p] = ch.status;
+    heads[p].status = ch.status;
+    if (ch.status == BP_PROOF_OK) rp_scalars_head(heads[p], ch, proof, g.k, g.n, g.m);
+}
+// K5: verification scalars, fully data-parallel: one thread per (proof, term) with term in
+// [0, N) -> (g_i, h_i) and [N, N + D) -> the per-proof scalars.
+//   contrib : count x S Montgomery scalars (weighted static-term scalars: B~, B, G.., H..)
+//   dyn     : count x D canonical scalars, written straight into the MSM scalar array
+__global__ void __launch_bounds__(128) k_rp_scalars(rp_geom g, const rp_head *__restrict__ heads, uint32_t count,
+                                                    sc *__restrict__ contrib, uint8_t *__restrict__ dyn_scalars) {
+    uint32_t per = g.N + g.D;
+    size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= (size_t)count * per) return;
+    uint32_t p = (uint32_t)(gi / per), i = (uint32_t)(gi % per);
+    const rp_head &h = heads[p];
     sc *my = contrib + (size_t)p * g.S;
     uint8_t *dyn = dyn_scalars + (size_t)p * g.D * 32;
-    if (h.status != BP_PROOF_OK) {            // malformed proof: contributes nothing to the combination
-        for (uint32_t i = threadIdx.x; i < g.S; i += blockDim.x) my[i] = sc_zero();
-        for (uint32_t i = threadIdx.x; i < g.D * 8; i += blockDim.x) reinterpret_cast<uint32_t *>(dyn)[i] = 0;
-        return;
-    }
-    if (threadIdx.x == 0) { my[0] = h.blinding_scalar; my[1] = h.basepoint_scalar; }
-    for (uint32_t i = threadIdx.x; i < g.N; i += blockDim.x) {
-        sc gi, hi; rp_prep_gh(h, i, g.k, g.n, gi, hi);
-        my[2 + i] = gi; my[2 + g.N + i] = hi;
-    }
-    for (uint32_t i = threadIdx.x; i < g.D; i += blockDim.x) {
-        sc v = sc_from_mont(rp_prep_dynamic(h, i, g.k));
-        uint8_t b[32]; sc_store(b, v); st32(dyn + 32 * i, b);
+    bool ok = h.status == BP_PROOF_OK;        // a malformed proof contributes nothing to the combination
+    if (i < g.N) {
+        sc gg = sc_zero(), hh = sc_zero();
+        if (ok) rp_scalars_gh(h, i, g.k, g.n, gg, hh);
+        my[2 + i] = gg; my[2 + g.N + i] = hh;
+        if (i == 0) { my[0] = ok ? h.blinding_scalar : sc_zero(); my[1] = ok ? h.basepoint_scalar : sc_zero(); }
+    } else {
+        uint32_t d = i - g.N;
+        sc v = ok ? sc_from_mont(rp_scalars_dynamic(h, d, g.k)) : sc_zero();
+        uint8_t b[32]; sc_store(b, v); st32(dyn + 32 * d, b);
     }
 }
 // decompress the per-proof points in MSM order A,S,T_1,T_2,L..,R..,V.. straight out of the proof bytes

@@ -54,35 +54,37 @@ BP_HD void keccak_f1600(uint64_t s[25]) {
 // Serialized transcript state = what crosses the C ABI: 200 state bytes, pos, pos_begin, cur_flags
 #define BP_TRANSCRIPT_BYTES 203
 
-struct merlin_t {
-    uint64_t st[25];       // little-endian byte view of the 200-byte state
-    uint32_t pos, pos_begin, cur_flags;
-};
+// The 200 state bytes live wherever the caller puts them (a local array on the host, a padded
+// shared-memory row on the device); st must be 4-byte aligned.
+struct merlin_t { uint8_t *st; uint32_t pos, pos_begin, cur_flags; };
 
-BP_HD uint8_t merlin_get(const merlin_t &m, uint32_t i) { return (uint8_t)(m.st[i >> 3] >> (8 * (i & 7))); }
-BP_HD void merlin_xor(merlin_t &m, uint32_t i, uint8_t b) { m.st[i >> 3] ^= (uint64_t)b << (8 * (i & 7)); }
-BP_HD void merlin_set(merlin_t &m, uint32_t i, uint8_t b) { m.st[i >> 3] = (m.st[i >> 3] & ~(0xffULL << (8 * (i & 7)))) | ((uint64_t)b << (8 * (i & 7))); }
-
+BP_HD void strobe_permute(merlin_t &m) {
+    uint32_t *w32 = reinterpret_cast<uint32_t *>(m.st);
+    uint64_t w[25];
+    for (int i = 0; i < 25; i++) w[i] = (uint64_t)w32[2 * i] | ((uint64_t)w32[2 * i + 1] << 32);
+    keccak_f1600(w);
+    for (int i = 0; i < 25; i++) { w32[2 * i] = (uint32_t)w[i]; w32[2 * i + 1] = (uint32_t)(w[i] >> 32); }
+}
 BP_HD void merlin_load(merlin_t &m, const uint8_t *ser) {
-    for (int i = 0; i < 25; i++) { uint64_t w = 0; for (int j = 0; j < 8; j++) w |= (uint64_t)ser[8 * i + j] << (8 * j); m.st[i] = w; }
+    for (int i = 0; i < 200; i++) m.st[i] = ser[i];
     m.pos = ser[200]; m.pos_begin = ser[201]; m.cur_flags = ser[202];
 }
 BP_HD void merlin_store(uint8_t *ser, const merlin_t &m) {
-    for (int i = 0; i < 200; i++) ser[i] = merlin_get(m, i);
+    for (int i = 0; i < 200; i++) ser[i] = m.st[i];
     ser[200] = (uint8_t)m.pos; ser[201] = (uint8_t)m.pos_begin; ser[202] = (uint8_t)m.cur_flags;
 }
-BP_HD void strobe_run_f(merlin_t &m) {
-    merlin_xor(m, m.pos, (uint8_t)m.pos_begin);
-    merlin_xor(m, m.pos + 1, 0x04);
-    merlin_xor(m, BP_STROBE_R + 1, 0x80);
-    keccak_f1600(m.st);
+BP_HDN void strobe_run_f(merlin_t &m) {
+    m.st[m.pos] ^= (uint8_t)m.pos_begin;
+    m.st[m.pos + 1] ^= 0x04;
+    m.st[BP_STROBE_R + 1] ^= 0x80;
+    strobe_permute(m);
     m.pos = 0; m.pos_begin = 0;
 }
-BP_HD void strobe_absorb(merlin_t &m, const uint8_t *d, uint32_t n) {
-    for (uint32_t i = 0; i < n; i++) { merlin_xor(m, m.pos, d[i]); if (++m.pos == BP_STROBE_R) strobe_run_f(m); }
+BP_HDN void strobe_absorb(merlin_t &m, const uint8_t *d, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) { m.st[m.pos] ^= d[i]; if (++m.pos == BP_STROBE_R) strobe_run_f(m); }
 }
-BP_HD void strobe_squeeze(merlin_t &m, uint8_t *d, uint32_t n) {
-    for (uint32_t i = 0; i < n; i++) { d[i] = merlin_get(m, m.pos); merlin_set(m, m.pos, 0); if (++m.pos == BP_STROBE_R) strobe_run_f(m); }
+BP_HDN void strobe_squeeze(merlin_t &m, uint8_t *d, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) { d[i] = m.st[m.pos]; m.st[m.pos] = 0; if (++m.pos == BP_STROBE_R) strobe_run_f(m); }
 }
 BP_HD void strobe_begin_op(merlin_t &m, uint8_t flags) {
     uint8_t hdr[2] = { (uint8_t)m.pos_begin, flags };
@@ -91,7 +93,7 @@ BP_HD void strobe_begin_op(merlin_t &m, uint8_t flags) {
     if ((flags & (4 | 32)) && m.pos != 0) strobe_run_f(m);       // C or K flag forces a permutation
 }
 // label must be a NUL-terminated ASCII string
-BP_HD void merlin_append(merlin_t &m, const char *label, const uint8_t *msg, uint32_t len) {
+BP_HDN void merlin_append(merlin_t &m, const char *label, const uint8_t *msg, uint32_t len) {
     uint32_t ll = 0; while (label[ll]) ll++;
     uint8_t l4[4] = { (uint8_t)len, (uint8_t)(len >> 8), (uint8_t)(len >> 16), (uint8_t)(len >> 24) };
     strobe_begin_op(m, 16 | 2); strobe_absorb(m, (const uint8_t *)label, ll);   // meta_ad(label)
@@ -102,7 +104,7 @@ BP_HD void merlin_append_u64(merlin_t &m, const char *label, uint64_t x) {
     uint8_t b[8]; for (int i = 0; i < 8; i++) b[i] = (uint8_t)(x >> (8 * i));
     merlin_append(m, label, b, 8);
 }
-BP_HD void merlin_challenge(merlin_t &m, const char *label, uint8_t *out, uint32_t len) {
+BP_HDN void merlin_challenge(merlin_t &m, const char *label, uint8_t *out, uint32_t len) {
     uint32_t ll = 0; while (label[ll]) ll++;
     uint8_t l4[4] = { (uint8_t)len, (uint8_t)(len >> 8), (uint8_t)(len >> 16), (uint8_t)(len >> 24) };
     strobe_begin_op(m, 16 | 2); strobe_absorb(m, (const uint8_t *)label, ll);
@@ -111,10 +113,10 @@ BP_HD void merlin_challenge(merlin_t &m, const char *label, uint8_t *out, uint32
 }
 // Transcript::new(label): STROBE init, meta_ad("Merlin v1.0"), then append_message("dom-sep", label)
 BP_HD void merlin_init(merlin_t &m, const uint8_t *label, uint32_t len) {
-    for (int i = 0; i < 25; i++) m.st[i] = 0;
+    for (int i = 0; i < 200; i++) m.st[i] = 0;
     const uint8_t hdr[18] = { 1, BP_STROBE_R + 2, 1, 0, 1, 96, 'S', 'T', 'R', 'O', 'B', 'E', 'v', '1', '.', '0', '.', '2' };
-    for (int i = 0; i < 18; i++) merlin_xor(m, i, hdr[i]);
-    keccak_f1600(m.st);
+    for (int i = 0; i < 18; i++) m.st[i] = hdr[i];
+    strobe_permute(m);
     m.pos = 0; m.pos_begin = 0; m.cur_flags = 0;
     const char proto[] = "Merlin v1.0";
     strobe_begin_op(m, 16 | 2); strobe_absorb(m, (const uint8_t *)proto, 11);

@@ -4,12 +4,20 @@
 //   /root/reference/src/range_proof/mod.rs:368-419 (transcript replay, scalar assembly),
 //   /root/reference/src/inner_product_proof.rs:198-253 (verification_scalars),
 //   /root/reference/src/range_proof/mod.rs:587-593 (delta),
-// and multiplies every scalar by a per-proof random weight rho so that a batch of proofs can be
-// checked with one random-linear-combination MSM.
+// with two changes that do not alter any verdict:
+//  (1) every scalar of proof i is multiplied by a per-proof random weight, so that a batch of
+//      proofs is checked with one random-linear-combination MSM;
+//  (2) the weight is rho * lambda with lambda = (prod u_j)^2 * y^(N-1).  Multiplying the whole
+//      mega-check by lambda cancels every inverse the reference computes (y^-i, u_j^-2, the
+//      batch_invert product), so no field inversion is needed on the device:
+//        lambda * u_j^-2          = y^(N-1) * prod_{j' != j} u_j'^2
+//        lambda * s_i             = U * y^(N-1) * prod_{bits set in i} u^2      (U = prod u_j)
+//        lambda * y^-i * s_{N-1-i} = U * y^(N-1-i) * prod_{bits clear in i} u^2
+//      lambda != 0 with overwhelming probability and rho is uniform, so rho*lambda is a uniform weight.
 //
-// The work is split in a sequential head (one thread: transcript, one field inversion) and a
-// data-parallel tail (one index i of the N = n*m generator pairs per thread).  All scalars are in
-// Montgomery form between the byte boundaries.
+// The work is split in a transcript replay (one thread per proof: Keccak chain), a short
+// sequential head (one thread: ~8k+30 products) and a data-parallel tail (one generator index per
+// thread).  All scalars are in Montgomery form between the byte boundaries.
 #pragma once
 #include "sc.cuh"
 #include "merlin.cuh"
@@ -19,128 +27,134 @@
 #define BP_PROOF_VERIFICATION_ERROR 1
 #define BP_PROOF_FORMAT_ERROR 2
 
-#define BP_MAX_LG_N 20          // verify up to N = n*m = 2^20 generator pairs per proof (R1CS-sized)
+#define BP_MAX_LG_N 20          // N = n*m up to 2^20 generator pairs per proof
 
-struct rp_head {
-    // challenges and derived values, Montgomery form
-    sc y_inv, z, zz, x, w, c, rho;
-    sc a, b, t_x, t_x_bl, e_bl;
-    sc s0;                                  // allinv = prod u_j^-1
-    sc u_sq[BP_MAX_LG_N], u_inv_sq[BP_MAX_LG_N];
-    sc y_inv_pow2[BP_MAX_LG_N];             // y^-(2^b)
-    sc basepoint_scalar, blinding_scalar;   // weighted by rho
+// out-of-line Montgomery product: one copy of the three-pass multiplier per kernel
+BP_HDN sc sc_mm(const sc &a, const sc &b) { return sc_mont_mul(a, b); }
+
+struct rp_challenges {          // Montgomery form
+    sc y, z, x, w, c, rho;
+    sc u[BP_MAX_LG_N];
     uint32_t status;
 };
 
 BP_HD bool bp_is_zero32(const uint8_t *p) { uint8_t z = 0; for (int i = 0; i < 32; i++) z |= p[i]; return z == 0; }
+BP_HD sc rp_wide(const uint8_t buf[64]) { sc lo = sc_load(buf), hi = sc_load(buf + 32); return sc_add(sc_mm(lo, sc{SC_RR_LIMBS}), sc_mm(hi, sc{SC_RRR_LIMBS})); }
+BP_HD sc rp_challenge(merlin_t &t, const char *label) { uint8_t buf[64]; merlin_challenge(t, label, buf, 64); return rp_wide(buf); }
 
-BP_HD sc rp_challenge(merlin_t &t, const char *label) { uint8_t buf[64]; merlin_challenge(t, label, buf, 64); return sc_mont_from_wide(buf); }
-BP_HD void rp_append_scalar(merlin_t &t, const char *label, const uint8_t *b) { merlin_append(t, label, b, 32); }
-
-// sum_{i<n} x^i for n a power of two (util.rs:240-256), Montgomery form
-BP_HD sc rp_sum_of_powers_pow2(const sc &x, uint64_t n) {
-    if (n == 1) return sc_mont_one();
-    sc result = sc_add(sc_mont_one(), x), factor = x;
-    for (uint64_t m = n; m > 2; m >>= 1) { factor = sc_mont_mul(factor, factor); result = sc_add(result, sc_mont_mul(factor, result)); }
-    return result;
-}
-
-// Sequential head.  proof = 32*(9+2k) bytes, V = m*32 bytes, tstate = serialized transcript the caller
-// passed in (state after Transcript::new(label) and any application messages), weights = 128 bytes
-// of per-proof randomness (c from the first 64, rho from the last 64).
-BP_HDN void rp_prep_head(rp_head &h, const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t n, uint32_t m,
-                         const uint8_t *tstate, const uint8_t *weights) {
-    h.status = BP_PROOF_OK;
+// Transcript replay of one proof.  proof = 32*(9+2k) bytes, V = m*32 bytes, tstate = the serialized
+// transcript the caller passed in, weights = 128 bytes of per-proof randomness (c, rho),
+// state200 = 200 bytes of 4-byte-aligned scratch for the STROBE state.
+BP_HDN void rp_transcript(rp_challenges &ch, const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t n, uint32_t m,
+                         const uint8_t *tstate, const uint8_t *weights, uint8_t *state200) {
+    ch.status = BP_PROOF_OK;
     const uint8_t *A = proof, *S = proof + 32, *T1 = proof + 64, *T2 = proof + 96;
     const uint8_t *LR = proof + 224, *ab = proof + 224 + 64 * k;
     // RangeProof::from_bytes / InnerProductProof::from_bytes canonicity (mod.rs:519-524, inner_product_proof.rs:399-404)
-    sc t_x = sc_load(proof + 128), t_x_bl = sc_load(proof + 160), e_bl = sc_load(proof + 192), a = sc_load(ab), b = sc_load(ab + 32);
-    if (sc_geq_l(t_x) || sc_geq_l(t_x_bl) || sc_geq_l(e_bl) || sc_geq_l(a) || sc_geq_l(b)) { h.status = BP_PROOF_FORMAT_ERROR; return; }
-
-    merlin_t t; merlin_load(t, tstate);
+    if (sc_geq_l(sc_load(proof + 128)) || sc_geq_l(sc_load(proof + 160)) || sc_geq_l(sc_load(proof + 192)) || sc_geq_l(sc_load(ab)) || sc_geq_l(sc_load(ab + 32))) {
+        ch.status = BP_PROOF_FORMAT_ERROR; return;
+    }
+    merlin_t t; t.st = state200; merlin_load(t, tstate);
     merlin_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);            // transcript.rs:44-48
     merlin_append_u64(t, "n", n); merlin_append_u64(t, "m", m);
     for (uint32_t j = 0; j < m; j++) merlin_append(t, "V", V + 32 * j, 32);         // mod.rs:370-374 (identity allowed)
     bool bad = bp_is_zero32(A) || bp_is_zero32(S);                                  // validate_and_append_point
     merlin_append(t, "A", A, 32); merlin_append(t, "S", S, 32);
-    sc y = rp_challenge(t, "y"); h.z = rp_challenge(t, "z");
+    ch.y = rp_challenge(t, "y"); ch.z = rp_challenge(t, "z");
     bad = bad || bp_is_zero32(T1) || bp_is_zero32(T2);
     merlin_append(t, "T_1", T1, 32); merlin_append(t, "T_2", T2, 32);
-    h.x = rp_challenge(t, "x");
-    rp_append_scalar(t, "t_x", proof + 128); rp_append_scalar(t, "t_x_blinding", proof + 160); rp_append_scalar(t, "e_blinding", proof + 192);
-    h.w = rp_challenge(t, "w");
+    ch.x = rp_challenge(t, "x");
+    merlin_append(t, "t_x", proof + 128, 32); merlin_append(t, "t_x_blinding", proof + 160, 32); merlin_append(t, "e_blinding", proof + 192, 32);
+    ch.w = rp_challenge(t, "w");
     merlin_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6);                      // transcript.rs:50-53
     merlin_append_u64(t, "n", (uint64_t)n * m);
-    sc u[BP_MAX_LG_N];
     for (uint32_t j = 0; j < k; j++) {                                              // inner_product_proof.rs:218-222
         bad = bad || bp_is_zero32(LR + 64 * j) || bp_is_zero32(LR + 64 * j + 32);
         merlin_append(t, "L", LR + 64 * j, 32); merlin_append(t, "R", LR + 64 * j + 32, 32);
-        u[j] = rp_challenge(t, "u");
+        ch.u[j] = rp_challenge(t, "u");
     }
-    if (bad) { h.status = BP_PROOF_VERIFICATION_ERROR; return; }
+    if (bad) { ch.status = BP_PROOF_VERIFICATION_ERROR; return; }
+    ch.c = rp_wide(weights); ch.rho = rp_wide(weights + 64);
+}
 
-    h.c = sc_mont_from_wide(weights); h.rho = sc_mont_from_wide(weights + 64);
-    h.a = sc_to_mont(a); h.b = sc_to_mont(b); h.t_x = sc_to_mont(t_x); h.t_x_bl = sc_to_mont(t_x_bl); h.e_bl = sc_to_mont(e_bl);
-    h.zz = sc_mont_mul(h.z, h.z);
+struct rp_head {                // Montgomery form; "L" = Lambda = rho * lambda
+    uint32_t status, pad_[7];
+    sc z, zz, L, zL, Lx, Lcx, Lcxx, Lczz, gA, hA, hB, rhoY;
+    sc u_sq[BP_MAX_LG_N], ypow2[BP_MAX_LG_N], pre[BP_MAX_LG_N + 1], suf[BP_MAX_LG_N + 1];
+    sc basepoint_scalar, blinding_scalar;
+};
 
-    // one inversion for y and all u_j (Montgomery's trick); a zero challenge has probability ~2^-252:
-    // dalek's invert() maps 0 to 0, and so does this (the product chain simply stays 0)
-    sc pre[BP_MAX_LG_N + 1];
-    sc acc = y;
-    for (uint32_t j = 0; j < k; j++) { pre[j] = acc; acc = sc_mont_mul(acc, u[j]); }
-    sc inv = sc_mont_invert(acc);
-    sc allinv = sc_mont_one();
-    for (int j = (int)k - 1; j >= 0; j--) {
-        sc ui = sc_mont_mul(inv, pre[j]);          // u_j^-1
-        inv = sc_mont_mul(inv, u[j]);
-        allinv = sc_mont_mul(allinv, ui);
-        h.u_sq[j] = sc_mont_mul(u[j], u[j]); h.u_inv_sq[j] = sc_mont_mul(ui, ui);
+// sum_{i<n} x^i for n a power of two (util.rs:240-256), Montgomery form
+BP_HD sc rp_sum_of_powers_pow2(const sc &x, uint64_t n) {
+    if (n == 1) return sc_mont_one();
+    sc result = sc_add(sc_mont_one(), x), factor = x;
+    for (uint64_t m = n; m > 2; m >>= 1) { factor = sc_mm(factor, factor); result = sc_add(result, sc_mm(factor, result)); }
+    return result;
+}
+
+// Sequential head: shared products of one proof
+BP_HDN void rp_scalars_head(rp_head &h, const rp_challenges &ch, const uint8_t *proof, uint32_t k, uint32_t n, uint32_t m) {
+    const uint8_t *ab = proof + 224 + 64 * k;
+    sc a = sc_to_mont(sc_load(ab)), b = sc_to_mont(sc_load(ab + 32));
+    sc t_x = sc_to_mont(sc_load(proof + 128)), t_x_bl = sc_to_mont(sc_load(proof + 160)), e_bl = sc_to_mont(sc_load(proof + 192));
+    h.z = ch.z; h.zz = sc_mm(ch.z, ch.z);
+    sc U = sc_mont_one(), Y = sc_mont_one();
+    h.pre[0] = sc_mont_one();
+    for (uint32_t j = 0; j < k; j++) {
+        h.u_sq[j] = sc_mm(ch.u[j], ch.u[j]); U = sc_mm(U, ch.u[j]);
+        h.pre[j + 1] = sc_mm(h.pre[j], h.u_sq[j]);                  // prod_{j' <= j} u^2;  pre[k] = U^2
+        h.ypow2[j] = j == 0 ? ch.y : sc_mm(h.ypow2[j - 1], h.ypow2[j - 1]);   // y^(2^j)
+        Y = sc_mm(Y, h.ypow2[j]);                                   // ends as y^(N-1)
     }
-    h.y_inv = inv; h.s0 = allinv;
-    h.y_inv_pow2[0] = h.y_inv;
-    for (uint32_t bb = 1; bb < k; bb++) h.y_inv_pow2[bb] = sc_mont_mul(h.y_inv_pow2[bb - 1], h.y_inv_pow2[bb - 1]);
-
+    h.suf[k] = sc_mont_one();
+    for (int j = (int)k - 1; j >= 0; j--) h.suf[j] = sc_mm(h.suf[j + 1], h.u_sq[j]);   // prod_{j' >= j} u^2
+    sc lambda = sc_mm(h.pre[k], Y);
+    h.L = sc_mm(ch.rho, lambda); h.zL = sc_mm(ch.z, h.L);
+    h.Lx = sc_mm(h.L, ch.x); h.Lcx = sc_mm(h.Lx, ch.c); h.Lcxx = sc_mm(h.Lcx, ch.x); h.Lczz = sc_mm(sc_mm(h.L, ch.c), h.zz);
+    sc rhoU = sc_mm(ch.rho, U);
+    h.gA = sc_mm(sc_mm(a, rhoU), Y);                                // a rho U y^(N-1)
+    h.hB = sc_mm(b, rhoU);                                          // b rho U
+    h.hA = sc_mm(sc_mm(rhoU, U), h.zz);                             // rho U^2 z^2
+    h.rhoY = sc_mm(ch.rho, Y);
     // delta(y,z) = (z - z^2) sum y^i - z^3 (2^n - 1) sum z^j          (mod.rs:587-593)
-    sc sum_y = rp_sum_of_powers_pow2(y, (uint64_t)n * m), sum_z = rp_sum_of_powers_pow2(h.z, m);
+    sc sum_y = rp_sum_of_powers_pow2(ch.y, (uint64_t)n * m), sum_z = rp_sum_of_powers_pow2(ch.z, m);
     sc sum_2 = sc_mont_from_u64(n == 64 ? ~0ULL : ((1ULL << n) - 1));
-    sc delta = sc_sub(sc_mont_mul(sc_sub(h.z, h.zz), sum_y), sc_mont_mul(sc_mont_mul(sc_mont_mul(h.zz, h.z), sum_2), sum_z));
+    sc delta = sc_sub(sc_mm(sc_sub(ch.z, h.zz), sum_y), sc_mm(sc_mm(sc_mm(h.zz, ch.z), sum_2), sum_z));
     // basepoint scalar w (t_x - a b) + c (delta - t_x)  (mod.rs:419);  blinding scalar -e~ - c t~  (mod.rs:430)
-    sc bs = sc_add(sc_mont_mul(h.w, sc_sub(h.t_x, sc_mont_mul(h.a, h.b))), sc_mont_mul(h.c, sc_sub(delta, h.t_x)));
-    sc bl = sc_neg(sc_add(h.e_bl, sc_mont_mul(h.c, h.t_x_bl)));
-    h.basepoint_scalar = sc_mont_mul(h.rho, bs); h.blinding_scalar = sc_mont_mul(h.rho, bl);
+    sc bs = sc_add(sc_mm(ch.w, sc_sub(t_x, sc_mm(a, b))), sc_mm(ch.c, sc_sub(delta, t_x)));
+    sc bl = sc_neg(sc_add(e_bl, sc_mm(ch.c, t_x_bl)));
+    h.basepoint_scalar = sc_mm(h.L, bs); h.blinding_scalar = sc_mm(h.L, bl);
+}
+
+BP_HD sc rp_pow_small(const sc &base0, uint32_t e) {                // base^e by square-and-multiply
+    sc r = sc_mont_one(), base = base0;
+    for (; e; e >>= 1) { if (e & 1u) r = sc_mm(r, base); if (e > 1) base = sc_mm(base, base); }
+    return r;
 }
 
 // Data-parallel tail: weighted g_i and h_i for generator pair i in [0, N) (mod.rs:415-417), Montgomery form
-BP_HD void rp_prep_gh(const rp_head &h, uint32_t i, uint32_t k, uint32_t n, sc &g, sc &hh) {
-    sc s = h.s0, s_rev = h.s0, yi = sc_mont_one();
+BP_HD void rp_scalars_gh(const rp_head &h, uint32_t i, uint32_t k, uint32_t n, sc &g, sc &hh) {
+    sc s = sc_mont_one(), s_rev = sc_mont_one(), yy = sc_mont_one();
+    bool s1 = true, r1 = true, y1 = true;                           // skip multiplications by one
     for (uint32_t bb = 0; bb < k; bb++) {
-        // s_i = s_0 * prod_{bits b set in i} u_sq[(k-1)-b]  (inner_product_proof.rs:241-250);  s_{N-1-i} uses the clear bits
-        if ((i >> bb) & 1u) { s = sc_mont_mul(s, h.u_sq[(k - 1) - bb]); yi = sc_mont_mul(yi, h.y_inv_pow2[bb]); }
-        else s_rev = sc_mont_mul(s_rev, h.u_sq[(k - 1) - bb]);
+        const sc &usq = h.u_sq[(k - 1) - bb];                       // bit bb of i <-> challenge k-1-bb (inner_product_proof.rs:241-250)
+        if ((i >> bb) & 1u) { s = s1 ? usq : sc_mm(s, usq); s1 = false; }
+        else { s_rev = r1 ? usq : sc_mm(s_rev, usq); r1 = false; yy = y1 ? h.ypow2[bb] : sc_mm(yy, h.ypow2[bb]); y1 = false; }
     }
     uint32_t j = i / n, ii = i % n;
-    sc zj = sc_mont_one();                         // z^j by square-and-multiply
-    { sc base = h.z; for (uint32_t e = j; e; e >>= 1) { if (e & 1u) zj = sc_mont_mul(zj, base); base = sc_mont_mul(base, base); } }
-    sc two_i = sc_mont_from_u64(1ULL << ii);
-    sc gi = sc_sub(sc_neg(h.z), sc_mont_mul(h.a, s));
-    sc hi = sc_add(h.z, sc_mont_mul(yi, sc_sub(sc_mont_mul(sc_mont_mul(h.zz, zj), two_i), sc_mont_mul(h.b, s_rev))));
-    g = sc_mont_mul(h.rho, gi); hh = sc_mont_mul(h.rho, hi);
+    sc zj2 = sc_mm(rp_pow_small(h.z, j), sc_mont_from_u64(1ULL << ii));      // z^j 2^i'
+    g = sc_sub(sc_neg(h.zL), sc_mm(h.gA, s));
+    hh = sc_add(h.zL, sc_mm(yy, sc_sub(sc_mm(h.hA, zj2), sc_mm(h.hB, s_rev))));
 }
 
 // Per-proof ("dynamic") scalars in MSM order A, S, T_1, T_2, L_0..L_{k-1}, R_0..R_{k-1}, V_0..V_{m-1}
-// (mod.rs:422-444 without the static B~, B, G, H block); idx in [0, 4+2k+m); canonical bytes out
-BP_HD sc rp_prep_dynamic(const rp_head &h, uint32_t idx, uint32_t k) {
-    sc v;
-    if (idx == 0) v = sc_mont_one();
-    else if (idx == 1) v = h.x;
-    else if (idx == 2) v = sc_mont_mul(h.c, h.x);
-    else if (idx == 3) v = sc_mont_mul(sc_mont_mul(h.c, h.x), h.x);
-    else if (idx < 4 + k) v = h.u_sq[idx - 4];
-    else if (idx < 4 + 2 * k) v = h.u_inv_sq[idx - 4 - k];
-    else {
-        uint32_t j = idx - 4 - 2 * k; sc zj = sc_mont_one(), base = h.z;
-        for (uint32_t e = j; e; e >>= 1) { if (e & 1u) zj = sc_mont_mul(zj, base); base = sc_mont_mul(base, base); }
-        v = sc_mont_mul(sc_mont_mul(h.c, h.zz), zj);
-    }
-    return sc_mont_mul(h.rho, v);
+// (mod.rs:422-444 without the static B~, B, G, H block); idx in [0, 4+2k+m); Montgomery form
+BP_HD sc rp_scalars_dynamic(const rp_head &h, uint32_t idx, uint32_t k) {
+    if (idx == 0) return h.L;
+    if (idx == 1) return h.Lx;
+    if (idx == 2) return h.Lcx;
+    if (idx == 3) return h.Lcxx;
+    if (idx < 4 + k) return sc_mm(h.L, h.u_sq[idx - 4]);
+    if (idx < 4 + 2 * k) { uint32_t j = idx - 4 - k; return sc_mm(h.rhoY, sc_mm(h.pre[j], h.suf[j + 1])); }
+    return sc_mm(h.Lczz, rp_pow_small(h.z, idx - 4 - 2 * k));
 }

@@ -12,6 +12,7 @@ struct sc { uint32_t v[8]; };
 
 #define SC_L_LIMBS {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu, 0x00000000u, 0x00000000u, 0x00000000u, 0x10000000u}
 #define SC_LFACTOR 0x12547e1bu     // -l^-1 mod 2^32
+#define SC_LPRIME_LIMBS {0x12547e1bu, 0xd2b51da3u, 0xfdba84ffu, 0xb1a206f2u, 0xffa36beau, 0x14e75438u, 0x6fe91836u, 0x9db6c6f2u}   // -l^-1 mod 2^256
 #define SC_R_LIMBS {0x8d98951du, 0xd6ec3174u, 0x737dcf70u, 0xc6ef5bf4u, 0xfffffffeu, 0xffffffffu, 0xffffffffu, 0x0fffffffu}
 #define SC_RR_LIMBS {0x449c0f01u, 0xa40611e3u, 0x68859347u, 0xd00e1ba7u, 0x17f5be65u, 0xceec73d2u, 0x7c309a3du, 0x0399411bu}
 #define SC_RRR_LIMBS {0x7b83a2dbu, 0x2a9e4968u, 0xaef7f3ecu, 0x278324e6u, 0x04ec5b65u, 0x8065dc6cu, 0x3599cec7u, 0x0e530b77u}
@@ -51,29 +52,39 @@ BP_HD bool sc_is_zero(const sc &a) { uint32_t z = 0; for (int i = 0; i < 8; i++)
 
 // Montgomery product a*b/R mod l; b < l, a < 2^256
 BP_HD sc sc_mont_mul(const sc &a, const sc &b) {
+#ifdef __CUDA_ARCH__
+    // three passes through the PTX 8x8 multiplier of fe.cuh (high ILP, short carry chains):
+    // t = a*b;  M = t_lo * (-l^-1) mod 2^256;  r = (t + M*l) / 2^256  (< 2l)
+    fe fa, fb, fl = fe{SC_L_LIMBS}, flp = fe{SC_LPRIME_LIMBS};
+    for (int i = 0; i < 8; i++) { fa.v[i] = a.v[i]; fb.v[i] = b.v[i]; }
+    uint32_t t[16], q[16], u[16];
+    fe_mul_wide(t, fa, fb);
+    fe tl; for (int i = 0; i < 8; i++) tl.v[i] = t[i];
+    fe_mul_wide(q, tl, flp);
+    fe M; for (int i = 0; i < 8; i++) M.v[i] = q[i];
+    fe_mul_wide(u, M, fl);
+    // low halves cancel to zero mod 2^256 with a carry of (t_lo != 0)
+    uint32_t nz = 0; for (int i = 0; i < 8; i++) nz |= t[i];
+    uint64_t c = nz ? 1 : 0;
+    sc r;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)t[8 + i] + u[8 + i]; r.v[i] = (uint32_t)c; c >>= 32; }
+    return sc_cond_sub_l(r);                      // sum < 2l < 2^254: c is zero here
+#else
     const sc l = sc_l();
     uint32_t t[10];
     for (int i = 0; i < 10; i++) t[i] = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
     for (int i = 0; i < 8; i++) {
         uint64_t c = 0;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
         for (int j = 0; j < 8; j++) { c += (uint64_t)a.v[j] * b.v[i] + t[j]; t[j] = (uint32_t)c; c >>= 32; }
         c += t[8]; t[8] = (uint32_t)c; t[9] = (uint32_t)(c >> 32);
         uint32_t m = t[0] * SC_LFACTOR;
         c = (uint64_t)m * l.v[0] + t[0]; c >>= 32;
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
         for (int j = 1; j < 8; j++) { c += (uint64_t)m * l.v[j] + t[j]; t[j - 1] = (uint32_t)c; c >>= 32; }
         c += t[8]; t[7] = (uint32_t)c; t[8] = t[9] + (uint32_t)(c >> 32);
     }
     sc r; for (int i = 0; i < 8; i++) r.v[i] = t[i];
     return sc_cond_sub_l(r);                      // t < 2l
+#endif
 }
 BP_HD sc sc_to_mont(const sc &a) { return sc_mont_mul(a, sc{SC_RR_LIMBS}); }
 BP_HD sc sc_from_mont(const sc &a) { sc one = sc_zero(); one.v[0] = 1; return sc_mont_mul(a, one); }

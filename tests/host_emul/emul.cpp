@@ -54,19 +54,20 @@ void emul_sc_addsub(const uint8_t *a, const uint8_t *b, int sub, uint8_t *out) {
 void emul_sc_invert(const uint8_t *a, uint8_t *out) { sc_store(out, sc_from_mont(sc_mont_invert(sc_to_mont(sc_load(a))))); }
 void emul_sc_from_wide(const uint8_t *in, uint8_t *out) { sc_store(out, sc_from_mont(sc_mont_from_wide(in))); }
 
-void emul_transcript_new(const uint8_t *label, uint32_t len, uint8_t *ser) { merlin_t m; merlin_init(m, label, len); merlin_store(ser, m); }
-void emul_transcript_append(uint8_t *ser, const char *label, const uint8_t *msg, uint32_t len) { merlin_t m; merlin_load(m, ser); merlin_append(m, label, msg, len); merlin_store(ser, m); }
-void emul_transcript_challenge(uint8_t *ser, const char *label, uint8_t *out, uint32_t len) { merlin_t m; merlin_load(m, ser); merlin_challenge(m, label, out, len); merlin_store(ser, m); }
+void emul_transcript_new(const uint8_t *label, uint32_t len, uint8_t *ser) { alignas(8) uint8_t st[200]; merlin_t m; m.st = st; merlin_init(m, label, len); merlin_store(ser, m); }
+void emul_transcript_append(uint8_t *ser, const char *label, const uint8_t *msg, uint32_t len) { alignas(8) uint8_t st[200]; merlin_t m; m.st = st; merlin_load(m, ser); merlin_append(m, label, msg, len); merlin_store(ser, m); }
+void emul_transcript_challenge(uint8_t *ser, const char *label, uint8_t *out, uint32_t len) { alignas(8) uint8_t st[200]; merlin_t m; m.st = st; merlin_load(m, ser); merlin_challenge(m, label, out, len); merlin_store(ser, m); }
 
 // full verification-scalar vector of one proof in the order [B~, B, G.., H.. | A,S,T1,T2,L..,R..,V..], canonical bytes
 int emul_rp_scalars(const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t n, uint32_t m, const uint8_t *tstate, const uint8_t *weights, uint8_t *out) {
-    static rp_head h;
-    rp_prep_head(h, proof, k, V, n, m, tstate, weights);
-    if (h.status) return (int)h.status;
+    static rp_head h; static rp_challenges ch; alignas(8) uint8_t st[200];
+    rp_transcript(ch, proof, k, V, n, m, tstate, weights, st);
+    if (ch.status) return (int)ch.status;
+    rp_scalars_head(h, ch, proof, k, n, m);
     uint32_t N = n * m, S = 2 + 2 * N, D = 4 + 2 * k + m;
     sc_store(out, sc_from_mont(h.blinding_scalar)); sc_store(out + 32, sc_from_mont(h.basepoint_scalar));
-    for (uint32_t i = 0; i < N; i++) { sc g, hh; rp_prep_gh(h, i, k, n, g, hh); sc_store(out + 32 * (2 + i), sc_from_mont(g)); sc_store(out + 32 * (2 + N + i), sc_from_mont(hh)); }
-    for (uint32_t i = 0; i < D; i++) sc_store(out + 32 * (S + i), sc_from_mont(rp_prep_dynamic(h, i, k)));
+    for (uint32_t i = 0; i < N; i++) { sc g, hh; rp_scalars_gh(h, i, k, n, g, hh); sc_store(out + 32 * (2 + i), sc_from_mont(g)); sc_store(out + 32 * (2 + N + i), sc_from_mont(hh)); }
+    for (uint32_t i = 0; i < D; i++) sc_store(out + 32 * (S + i), sc_from_mont(rp_scalars_dynamic(h, i, k)));
     return 0;
 }
 

@@ -49,7 +49,7 @@ struct bp_ctx {
     // MSM scratch
     DevBuf in_scalars, in_points, in_offsets, niels, ok, msm_err, counts, starts, cursor, sorted, buckets, wsums, results, outs, flags;
     // range-proof scratch
-    DevBuf rp_chal, rp_proofs, rp_commit, rp_tstate, rp_seed, rp_contrib, rp_scalars, rp_status, rp_pidx, rp_offsets, rp_verdict, rp_batch_ok;
+    DevBuf rp_chal, rp_tabs, pow2_tab, rp_proofs, rp_commit, rp_tstate, rp_seed, rp_contrib, rp_scalars, rp_status, rp_pidx, rp_offsets, rp_verdict, rp_batch_ok;
     DevBuf fb_scalars, fb_pidx, fb_offsets;
     uint32_t *h_verdict = nullptr; size_t h_verdict_cap = 0;       // pinned
     uint32_t *h_flag = nullptr;                                      // pinned, 4 words
@@ -179,7 +179,7 @@ void bp_ctx_destroy(bp_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     DevBuf *bufs[] = {&c->in_scalars, &c->in_points, &c->in_offsets, &c->niels, &c->ok, &c->msm_err, &c->counts, &c->starts, &c->cursor, &c->sorted, &c->buckets,
-                      &c->wsums, &c->results, &c->outs, &c->flags, &c->rp_chal, &c->rp_proofs, &c->rp_commit, &c->rp_tstate, &c->rp_seed, &c->rp_contrib, &c->rp_scalars,
+                      &c->wsums, &c->results, &c->outs, &c->flags, &c->rp_chal, &c->rp_tabs, &c->pow2_tab, &c->rp_proofs, &c->rp_commit, &c->rp_tstate, &c->rp_seed, &c->rp_contrib, &c->rp_scalars,
                       &c->rp_status, &c->rp_pidx, &c->rp_offsets, &c->rp_verdict, &c->rp_batch_ok, &c->fb_scalars, &c->fb_pidx, &c->fb_offsets};
     for (DevBuf *b : bufs) b->release();
     if (c->h_verdict) cudaFreeHost(c->h_verdict);
@@ -373,10 +373,16 @@ static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t 
     CK(c, cudaMemcpyAsync(c->rp_batch_ok.p, stage + 336, 4, cudaMemcpyHostToDevice, s));
 
     uint8_t *d_scal = c->rp_scalars.as<uint8_t>();
-    CK(c, c->rp_chal.ensure((size_t)count * sizeof(rp_head)));
+    CK(c, c->rp_chal.ensure((size_t)count * sizeof(rp_head))); CK(c, c->rp_tabs.ensure((size_t)count * rp_tab_size(g.k, g.m) * sizeof(sc)));
+    if (!c->pow2_tab.p) {            // 2^e (e < 64) in Montgomery form, computed once per context with the host build of sc.cuh
+        std::vector<sc> tab(64);
+        for (int e = 0; e < 64; e++) tab[e] = sc_mont_from_u64(1ULL << e);
+        CK(c, c->pow2_tab.ensure(64 * sizeof(sc)));
+        CK(c, cudaMemcpyAsync(c->pow2_tab.p, tab.data(), 64 * sizeof(sc), cudaMemcpyHostToDevice, s)); CK(c, cudaStreamSynchronize(s));
+    }
     LAUNCH(c, KID_RP_TRANSCRIPT, k_rp_transcript<<<blocks_for(count, RP_TR_THREADS), RP_TR_THREADS, 0, s>>>(d_proofs, d_commit, g, c->rp_tstate.as<uint8_t>(), c->rp_seed.as<uint8_t>(), count,
-                                                                                                           c->rp_chal.as<rp_head>(), c->rp_status.as<uint32_t>()));
-    LAUNCH(c, KID_RP_SCALARS, k_rp_scalars<<<blocks_for((size_t)count * (g.N + g.D), 128), 128, 0, s>>>(g, c->rp_chal.as<rp_head>(), count, c->rp_contrib.as<sc>(), d_scal + (size_t)g.S * 32));
+                                                                                                           c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(), c->rp_status.as<uint32_t>()));
+    LAUNCH(c, KID_RP_SCALARS, k_rp_scalars<<<blocks_for((size_t)count * (g.N + g.D), 128), 128, 0, s>>>(g, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(), c->pow2_tab.as<sc>(), count, c->rp_contrib.as<sc>(), d_scal + (size_t)g.S * 32));
     LAUNCH(c, KID_RP_DECOMPRESS, k_rp_decompress<<<blocks_for((size_t)count * g.D, 128), 128, 0, s>>>(d_proofs, d_commit, g, count, c->niels.as<ge_niels>(), c->rp_status.as<uint32_t>()));
     LAUNCH(c, KID_RP_STATIC_REDUCE, k_rp_static_reduce<<<g.S, 128, 0, s>>>(c->rp_contrib.as<sc>(), g.S, count, d_scal));
     LAUNCH(c, KID_SMALL, k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 0, c->rp_pidx.as<uint32_t>()));

@@ -79,10 +79,20 @@ BP_HDN void rp_transcript(rp_challenges &ch, const uint8_t *proof, uint32_t k, c
 
 struct rp_head {                // Montgomery form; "L" = Lambda = rho * lambda
     uint32_t status, pad_[7];
-    sc z, zz, L, zL, Lx, Lcx, Lcxx, Lczz, gA, hA, hB, rhoY;
-    sc u_sq[BP_MAX_LG_N], ypow2[BP_MAX_LG_N], pre[BP_MAX_LG_N + 1], suf[BP_MAX_LG_N + 1];
+    sc z, zz, L, zL, Lx, Lcx, Lcxx, Lczz, gA, hB, rhoY;
+    sc u_sq[BP_MAX_LG_N], pre[BP_MAX_LG_N + 1], suf[BP_MAX_LG_N + 1];
     sc basepoint_scalar, blinding_scalar;
 };
+
+// Per-proof product tables (global memory, rp_tab_size() scalars per proof) that turn the k-step
+// products of the tail into one lookup pair each.  The k index bits are split in a low group of
+// kl = ceil(k/2) bits and a high group of kh = k - kl bits:
+//   s_lo[v] = prod_{b < kl, bit b of v}  u_sq[k-1-b]        s_hi[v] = prod_{b < kh, bit b of v} u_sq[k-1-kl-b]
+//   y_lo[v] = y^v                                            y_hi[v] = y^(v * 2^kl)
+//   hAz[j]  = rho U^2 z^2 z^j   (j < m)
+// so that  prod_{bits set in i} u^2 = s_hi[i >> kl] * s_lo[i & (2^kl - 1)]  and  y^e likewise.
+BP_HD uint32_t rp_kl(uint32_t k) { return (k + 1) / 2; }
+BP_HD uint32_t rp_tab_size(uint32_t k, uint32_t m) { uint32_t kl = rp_kl(k); return 2 * ((1u << kl) + (1u << (k - kl))) + m; }
 
 // sum_{i<n} x^i for n a power of two (util.rs:240-256), Montgomery form
 BP_HD sc rp_sum_of_powers_pow2(const sc &x, uint64_t n) {
@@ -92,29 +102,48 @@ BP_HD sc rp_sum_of_powers_pow2(const sc &x, uint64_t n) {
     return result;
 }
 
-// Sequential head: shared products of one proof
-BP_HDN void rp_scalars_head(rp_head &h, const rp_challenges &ch, const uint8_t *proof, uint32_t k, uint32_t n, uint32_t m) {
+// table[v] for v in [0, 2^bits): product of f[b] over the set bits b of v; f(b) supplied by the caller
+#define RP_BUILD_TABLE(tab, bits, FACTOR)                                                    \
+    do {                                                                                     \
+        (tab)[0] = sc_mont_one();                                                            \
+        for (uint32_t b_ = 0; b_ < (bits); b_++) {                                           \
+            const sc f_ = (FACTOR);                                                          \
+            (tab)[1u << b_] = f_;                                                            \
+            for (uint32_t v_ = 1; v_ < (1u << b_); v_++) (tab)[(1u << b_) + v_] = sc_mm((tab)[v_], f_); \
+        }                                                                                    \
+    } while (0)
+
+// Sequential head: shared products and tables of one proof
+BP_HDN void rp_scalars_head(rp_head &h, sc *tab, const rp_challenges &ch, const uint8_t *proof, uint32_t k, uint32_t n, uint32_t m) {
     const uint8_t *ab = proof + 224 + 64 * k;
     sc a = sc_to_mont(sc_load(ab)), b = sc_to_mont(sc_load(ab + 32));
     sc t_x = sc_to_mont(sc_load(proof + 128)), t_x_bl = sc_to_mont(sc_load(proof + 160)), e_bl = sc_to_mont(sc_load(proof + 192));
     h.z = ch.z; h.zz = sc_mm(ch.z, ch.z);
-    sc U = sc_mont_one(), Y = sc_mont_one();
+    uint32_t kl = rp_kl(k), kh = k - kl, TL = 1u << kl, TH = 1u << kh;
+    sc *s_lo = tab, *s_hi = tab + TL, *y_lo = s_hi + TH, *y_hi = y_lo + TL, *hAz = y_hi + TH;
+    sc U = sc_mont_one(), Y = sc_mont_one(), ypow2[BP_MAX_LG_N];
     h.pre[0] = sc_mont_one();
     for (uint32_t j = 0; j < k; j++) {
         h.u_sq[j] = sc_mm(ch.u[j], ch.u[j]); U = sc_mm(U, ch.u[j]);
         h.pre[j + 1] = sc_mm(h.pre[j], h.u_sq[j]);                  // prod_{j' <= j} u^2;  pre[k] = U^2
-        h.ypow2[j] = j == 0 ? ch.y : sc_mm(h.ypow2[j - 1], h.ypow2[j - 1]);   // y^(2^j)
-        Y = sc_mm(Y, h.ypow2[j]);                                   // ends as y^(N-1)
+        ypow2[j] = j == 0 ? ch.y : sc_mm(ypow2[j - 1], ypow2[j - 1]);        // y^(2^j)
+        Y = sc_mm(Y, ypow2[j]);                                     // ends as y^(N-1)
     }
     h.suf[k] = sc_mont_one();
     for (int j = (int)k - 1; j >= 0; j--) h.suf[j] = sc_mm(h.suf[j + 1], h.u_sq[j]);   // prod_{j' >= j} u^2
+    // bit b of the index i <-> challenge k-1-b (inner_product_proof.rs:241-250)
+    RP_BUILD_TABLE(s_lo, kl, h.u_sq[(k - 1) - b_]);
+    RP_BUILD_TABLE(s_hi, kh, h.u_sq[(k - 1) - kl - b_]);
+    RP_BUILD_TABLE(y_lo, kl, ypow2[b_]);
+    RP_BUILD_TABLE(y_hi, kh, ypow2[kl + b_]);
     sc lambda = sc_mm(h.pre[k], Y);
     h.L = sc_mm(ch.rho, lambda); h.zL = sc_mm(ch.z, h.L);
     h.Lx = sc_mm(h.L, ch.x); h.Lcx = sc_mm(h.Lx, ch.c); h.Lcxx = sc_mm(h.Lcx, ch.x); h.Lczz = sc_mm(sc_mm(h.L, ch.c), h.zz);
     sc rhoU = sc_mm(ch.rho, U);
     h.gA = sc_mm(sc_mm(a, rhoU), Y);                                // a rho U y^(N-1)
     h.hB = sc_mm(b, rhoU);                                          // b rho U
-    h.hA = sc_mm(sc_mm(rhoU, U), h.zz);                             // rho U^2 z^2
+    hAz[0] = sc_mm(sc_mm(rhoU, U), h.zz);                           // rho U^2 z^2 z^j
+    for (uint32_t j = 1; j < m; j++) hAz[j] = sc_mm(hAz[j - 1], ch.z);
     h.rhoY = sc_mm(ch.rho, Y);
     // delta(y,z) = (z - z^2) sum y^i - z^3 (2^n - 1) sum z^j          (mod.rs:587-593)
     sc sum_y = rp_sum_of_powers_pow2(ch.y, (uint64_t)n * m), sum_z = rp_sum_of_powers_pow2(ch.z, m);
@@ -132,19 +161,18 @@ BP_HD sc rp_pow_small(const sc &base0, uint32_t e) {                // base^e by
     return r;
 }
 
-// Data-parallel tail: weighted g_i and h_i for generator pair i in [0, N) (mod.rs:415-417), Montgomery form
-BP_HD void rp_scalars_gh(const rp_head &h, uint32_t i, uint32_t k, uint32_t n, sc &g, sc &hh) {
-    sc s = sc_mont_one(), s_rev = sc_mont_one(), yy = sc_mont_one();
-    bool s1 = true, r1 = true, y1 = true;                           // skip multiplications by one
-    for (uint32_t bb = 0; bb < k; bb++) {
-        const sc &usq = h.u_sq[(k - 1) - bb];                       // bit bb of i <-> challenge k-1-bb (inner_product_proof.rs:241-250)
-        if ((i >> bb) & 1u) { s = s1 ? usq : sc_mm(s, usq); s1 = false; }
-        else { s_rev = r1 ? usq : sc_mm(s_rev, usq); r1 = false; yy = y1 ? h.ypow2[bb] : sc_mm(yy, h.ypow2[bb]); y1 = false; }
-    }
+// Data-parallel tail: weighted g_i and h_i for generator pair i in [0, N) (mod.rs:415-417), Montgomery form.
+// pow2 = table of 2^e (e < 64) in Montgomery form.  Seven products per index.
+BP_HD void rp_scalars_gh(const rp_head &h, const sc *tab, const sc *pow2, uint32_t i, uint32_t k, uint32_t n, sc &g, sc &hh) {
+    uint32_t kl = rp_kl(k), kh = k - kl, TL = 1u << kl, TH = 1u << kh;
+    const sc *s_lo = tab, *s_hi = tab + TL, *y_lo = s_hi + TH, *y_hi = y_lo + TL, *hAz = y_hi + TH;
+    uint32_t lo = i & (TL - 1), hi = i >> kl, nlo = lo ^ (TL - 1), nhi = hi ^ (TH - 1);
+    sc s = sc_mm(s_hi[hi], s_lo[lo]);                               // lambda-free s_i: prod over set bits
+    sc s_rev = sc_mm(s_hi[nhi], s_lo[nlo]);                         // prod over clear bits (= index N-1-i)
+    sc yy = sc_mm(y_hi[nhi], y_lo[nlo]);                            // y^(N-1-i)
     uint32_t j = i / n, ii = i % n;
-    sc zj2 = sc_mm(rp_pow_small(h.z, j), sc_mont_from_u64(1ULL << ii));      // z^j 2^i'
     g = sc_sub(sc_neg(h.zL), sc_mm(h.gA, s));
-    hh = sc_add(h.zL, sc_mm(yy, sc_sub(sc_mm(h.hA, zj2), sc_mm(h.hB, s_rev))));
+    hh = sc_add(h.zL, sc_mm(yy, sc_sub(sc_mm(hAz[j], pow2[ii]), sc_mm(h.hB, s_rev))));
 }
 
 // Per-proof ("dynamic") scalars in MSM order A, S, T_1, T_2, L_0..L_{k-1}, R_0..R_{k-1}, V_0..V_{m-1}

@@ -63,10 +63,12 @@ int emul_rp_scalars(const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t
     static rp_head h; static rp_challenges ch; alignas(8) uint8_t st[200];
     rp_transcript(ch, proof, k, V, n, m, tstate, weights, st);
     if (ch.status) return (int)ch.status;
-    rp_scalars_head(h, ch, proof, k, n, m);
+    std::vector<sc> tab(rp_tab_size(k, m)), pow2(64);
+    for (int e = 0; e < 64; e++) pow2[e] = sc_mont_from_u64(1ULL << e);
+    rp_scalars_head(h, tab.data(), ch, proof, k, n, m);
     uint32_t N = n * m, S = 2 + 2 * N, D = 4 + 2 * k + m;
     sc_store(out, sc_from_mont(h.blinding_scalar)); sc_store(out + 32, sc_from_mont(h.basepoint_scalar));
-    for (uint32_t i = 0; i < N; i++) { sc g, hh; rp_scalars_gh(h, i, k, n, g, hh); sc_store(out + 32 * (2 + i), sc_from_mont(g)); sc_store(out + 32 * (2 + N + i), sc_from_mont(hh)); }
+    for (uint32_t i = 0; i < N; i++) { sc g, hh; rp_scalars_gh(h, tab.data(), pow2.data(), i, k, n, g, hh); sc_store(out + 32 * (2 + i), sc_from_mont(g)); sc_store(out + 32 * (2 + N + i), sc_from_mont(hh)); }
     for (uint32_t i = 0; i < D; i++) sc_store(out + 32 * (S + i), sc_from_mont(rp_scalars_dynamic(h, i, k)));
     return 0;
 }

@@ -25,6 +25,9 @@ import sys
 import threading
 import time
 
+# one hardware work queue per stream (the default of 8 makes >8 streams share queues and serialise)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -121,7 +124,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--threads", type=int, default=1, help="host threads issuing steps (each drives streams/threads contexts)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -188,9 +192,24 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    from concurrent.futures import ThreadPoolExecutor
+    NT = max(1, min(args.threads, S))
+    pool = ThreadPoolExecutor(NT) if NT > 1 else None
+
+    def run_steps(step_fn, first, n):
+        """issue steps first..first+n-1; with several host threads, thread t issues the steps whose context index k = i % S has k % NT == t"""
+        if pool is None:
+            for i in range(first, first + n):
+                step_fn(i)
+            return
+        def worker(t):
+            for i in range(first, first + n):
+                if (i % S) % NT == t:
+                    step_fn(i)
+        list(pool.map(worker, range(NT)))
+
     def timed(step_fn, drain_fn, steps, warmup):
-        for i in range(warmup):
-            step_fn(i)
+        run_steps(step_fn, 0, warmup)
         drain_fn()
         barrier()
         l0 = sum(c.launches for c in ctxs)
@@ -200,8 +219,8 @@ def main():
         for s in streams[1:]:
             s.wait_event(start)
         t0 = time.perf_counter()
-        for i in range(steps):
-            step_fn(warmup + i)
+        run_steps(step_fn, warmup, steps)
+        host_issue = time.perf_counter() - t0
         drain_fn()
         for s, e in zip(streams, ends):
             e.record(s); streams[0].wait_event(e)
@@ -211,7 +230,7 @@ def main():
         ms = start.elapsed_time(end)
         if world > 1:
             tt = torch.tensor([ms], device="cuda"); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt.item())
-        return ms, wall, sum(c.launches for c in ctxs) - l0
+        return ms, wall, sum(c.launches for c in ctxs) - l0, host_issue
 
     # ---- value: inputs resident in HBM
     def step_dev(i):
@@ -219,7 +238,7 @@ def main():
         ver[k].run_device(d_proofs[j].data_ptr(), d_vs[j].data_ptr(), d_verdicts[k].data_ptr(), h_ok[k:].data_ptr())
 
     clk = ClockSampler(local); clk.start()
-    ms_dev, _, launches = timed(step_dev, lambda: None, args.steps, args.warmup)
+    ms_dev, _, launches, host_issue_dev = timed(step_dev, lambda: None, args.steps, args.warmup)
     clocks = clk.stop()
     assert int(h_ok.min()) == 1 and int(d_verdicts.abs().max()) == 0, "a timed batch did not verify"
     value = world * BATCH * args.steps / (ms_dev * 1e-3)
@@ -236,7 +255,7 @@ def main():
             if v.busy:
                 assert not any(v.finish())
 
-    ms_e2e, wall_e2e, _ = timed(step_e2e, drain_e2e, args.steps, args.warmup)
+    ms_e2e, wall_e2e, _, _ = timed(step_e2e, drain_e2e, args.steps, args.warmup)
     e2e_value = world * BATCH * args.steps / (max(ms_e2e * 1e-3, wall_e2e))
     h2d = BATCH * (plen + 32 * M_PARTIES) + bp.TRANSCRIPT_BYTES + 32 + 8 + 4
     d2h = 4 * BATCH + 4
@@ -268,7 +287,7 @@ def main():
     out = {"metric": "64-bit rangeproof verifications/sec (batched)", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (mod 2^255-19) / u32x8 (mod l)",
            "data": "synthetic (oracle-proved valid proofs over uniform 64-bit values)",
-           "config": {"workload": f"batched verify of {BATCH}x 64-bit RangeProofs (m=1) per GPU", "n": N_BITS, "m": M_PARTIES, "batch": BATCH, "streams": S,
+           "config": {"workload": f"batched verify of {BATCH}x 64-bit RangeProofs (m=1) per GPU", "n": N_BITS, "m": M_PARTIES, "batch": BATCH, "streams": S, "host_threads": NT, "host_issue_ms_per_step": round(1e3 * host_issue_dev / args.steps, 4),
                       "l2": f"inputs larger than L2: pool of {P} distinct input batches ({P * batch_bytes >> 20} MiB) cycled", "parallelism": f"independent batches per GPU x{world}"},
            "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": max(ms_e2e, wall_e2e * 1e3) / args.steps},
            "gpu_launches": launches, "clocks": clocks, "roofline": roofline}

@@ -29,6 +29,12 @@ SYMBOLS = {
     "bp_msm": (_int, [_vp, _u8p, _u8p, _sz, _u8p]),
     "bp_msm_batch": (_int, [_vp, _u8p, _u8p, _c.POINTER(_c.c_uint64), _sz, _u8p, _u8p]),
     "bp_msm_batch_device": (_int, [_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp]),
+    "bp_msm_indexed_batch": (_int, [_vp, _vp, _u8p, _c.POINTER(_c.c_uint32), _u8p, _sz, _c.POINTER(_c.c_uint64), _sz, _u8p, _u8p]),
+    "bp_ipp_begin": (_int, [_vp, _vp, _sz, _sz, _u8p, _c.POINTER(_vp)]),
+    "bp_ipp_begin_points": (_int, [_vp, _u8p, _u8p, _sz, _u8p, _c.POINTER(_vp)]),
+    "bp_ipp_lr": (_int, [_vp, _sz, _u8p, _u8p, _u8p, _u8p]),
+    "bp_ipp_fold": (_int, [_vp, _sz, _u8p, _u8p, _u8p, _u8p, _int]),
+    "bp_ipp_end": (None, [_vp]),
     "bp_gens_create": (_int, [_vp, _sz, _sz, _c.POINTER(_vp)]),
     "bp_gens_create_empty": (_int, [_vp, _sz, _sz, _c.POINTER(_vp)]),
     "bp_gens_destroy": (None, [_vp]),
@@ -73,6 +79,30 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
+
+
+HOST_LIB_PATH = os.path.join(_HERE, "libbulletproofs_host.so")
+_hlib = None
+
+
+def host_lib():
+    """C shim of the C++ mirror of the reference API (bulletproofs_b200/host): prover-side entry points."""
+    global _hlib
+    if _hlib is None:
+        lib()
+        if not os.path.exists(HOST_LIB_PATH):
+            raise ImportError(f"{HOST_LIB_PATH} is missing: run build()")
+        H = ctypes.CDLL(HOST_LIB_PATH)
+        H.bph_rangeproof_prove.restype = _int
+        H.bph_rangeproof_prove.argtypes = [_vp, _vp, _sz, _sz, _u8p, _c.POINTER(_c.c_uint64), _u8p, _sz, _sz, _u8p, _u8p, _u8p]
+        H.bph_rangeproof_verify.restype = _int
+        H.bph_rangeproof_verify.argtypes = [_vp, _vp, _sz, _sz, _u8p, _u8p, _sz, _u8p, _sz, _sz]
+        H.bph_ipp_create.restype = _int
+        H.bph_ipp_create.argtypes = [_vp, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _sz, _u8p]
+        H.bph_ipp_verify.restype = _int
+        H.bph_ipp_verify.argtypes = [_vp, _u8p, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _sz]
+        _hlib = H
+    return _hlib
 
 
 class Transcript:
@@ -255,6 +285,45 @@ class BatchVerifier:
         """device-resident inputs; nothing is synchronised (verdicts stay on the device)."""
         self.ctx._check(lib().bp_rangeproof_verify_batch_device(self.ctx._h, self.gens._h, self.t, d_proofs, self.proof_len, d_commitments,
                                                                 self.n, self.m, self.count, seed, d_verdicts_u32, h_batch_ok_pinned))
+
+
+def prove_multiple(ctx: Context, gens: Gens, transcript: Transcript, values, blindings: bytes, n: int, rng_seed: bytes):
+    """RangeProof::prove_multiple_with_rng with rng = ChaChaRng::from_seed(rng_seed) on the GPU-backed path.
+    Returns (status, proof bytes, commitments bytes); the transcript is advanced like the reference's &mut Transcript."""
+    m = len(values)
+    vals = (ctypes.c_uint64 * m)(*values)
+    proof = ctypes.create_string_buffer(rangeproof_size(n, m) if m and (n * m) & (n * m - 1) == 0 else 32 * 64)
+    V = ctypes.create_string_buffer(32 * max(m, 1))
+    rc = host_lib().bph_rangeproof_prove(ctx._h, gens._h, gens.gens_capacity, gens.party_capacity, transcript.state, vals, blindings, m, n, rng_seed, proof, V)
+    if rc < 0:
+        raise BpError(rc, lib().bp_last_error(ctx._h).decode())
+    return rc, proof.raw, V.raw
+
+
+def verify_multiple(ctx: Context, gens: Gens, transcript: Transcript, proof: bytes, commitments: bytes, n: int) -> int:
+    """RangeProof::from_bytes + verify_multiple through the C++ mirror; returns the ProofError code (0 = Ok)."""
+    m = len(commitments) // 32
+    rc = host_lib().bph_rangeproof_verify(ctx._h, gens._h, gens.gens_capacity, gens.party_capacity, transcript.to_bytes(), proof, len(proof), commitments, m, n)
+    if rc < 0:
+        raise BpError(rc, lib().bp_last_error(ctx._h).decode())
+    return rc
+
+
+def ipp_create(ctx: Context, transcript: Transcript, Q: bytes, Gf: bytes, Hf: bytes, G: bytes, H: bytes, a: bytes, b: bytes):
+    """InnerProductProof::create; returns the proof bytes (L_0,R_0,...,a,b) and advances the transcript."""
+    n = len(a) // 32
+    out = ctypes.create_string_buffer(32 * (2 * (n.bit_length() - 1) + 2))
+    rc = host_lib().bph_ipp_create(ctx._h, transcript.state, Q, Gf, Hf, G, H, a, b, n, out)
+    if rc != 0:
+        raise BpError(rc, lib().bp_last_error(ctx._h).decode())
+    return out.raw
+
+
+def ipp_verify(ctx: Context, transcript: Transcript, n: int, Gf: bytes, Hf: bytes, P: bytes, Q: bytes, G: bytes, H: bytes, proof: bytes) -> int:
+    rc = host_lib().bph_ipp_verify(ctx._h, transcript.state, n, Gf, Hf, P, Q, G, H, proof, len(proof))
+    if rc < 0:
+        raise BpError(rc, lib().bp_last_error(ctx._h).decode())
+    return rc
 
 
 def rangeproof_size(n: int, m: int) -> int:

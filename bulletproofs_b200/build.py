@@ -36,6 +36,17 @@ def build_cuda(force=False, verbose=False):
     return LIB
 
 
+def build_host(force=False):
+    """C++ mirror of the reference API (bulletproofs_b200/host), linked against libbpmsm.so"""
+    hdir = os.path.join(ROOT, "bulletproofs_b200", "host")
+    lib = os.path.join(ROOT, "bulletproofs_b200", "libbulletproofs_host.so")
+    srcs = [os.path.join(hdir, f) for f in os.listdir(hdir)] + [os.path.join(CSRC, f) for f in ("sc.cuh", "merlin.cuh", "fe.cuh")] + [LIB]
+    if force or not _newer(lib, srcs):
+        _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", lib, os.path.join(hdir, "bulletproofs.cpp"),
+              "-L" + os.path.join(ROOT, "bulletproofs_b200"), "-lbpmsm", "-Wl,-rpath,$ORIGIN"])
+    return lib
+
+
 def build_oracle(force=False):
     odir = os.path.join(ROOT, "oracle")
     lib = os.path.join(odir, "liboracle.so")
@@ -56,5 +67,6 @@ def build_emul(force=False):
 
 if __name__ == "__main__":
     build_cuda(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_host()
     build_oracle()
     build_emul()

@@ -4,6 +4,7 @@
 #include <sys/random.h>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -30,9 +31,9 @@ struct DevBuf {
 };
 
 enum KernelId { KID_DECOMPRESS, KID_COMPRESS, KID_FROM_UNIFORM, KID_MSM_COUNT, KID_MSM_SCAN, KID_MSM_SCATTER, KID_MSM_ACCUMULATE, KID_MSM_REDUCE,
-                KID_MSM_COMBINE, KID_RP_TRANSCRIPT, KID_RP_SCALARS, KID_RP_DECOMPRESS, KID_RP_STATIC_REDUCE, KID_SMALL, KID_COUNT };
+                KID_MSM_COMBINE, KID_RP_TRANSCRIPT, KID_RP_SCALARS, KID_RP_DECOMPRESS, KID_RP_STATIC_REDUCE, KID_IPP_FOLD, KID_SMALL, KID_COUNT };
 const char *const KERNEL_NAMES[KID_COUNT] = {"k_decompress", "k_compress", "k_from_uniform", "k_msm_count", "k_msm_scan", "k_msm_scatter", "k_msm_accumulate",
-                                             "k_msm_reduce", "k_msm_combine", "k_rp_transcript", "k_rp_scalars", "k_rp_decompress", "k_rp_static_reduce", "small_kernels"};
+                                             "k_msm_reduce", "k_msm_combine", "k_rp_transcript", "k_rp_scalars", "k_rp_decompress", "k_rp_static_reduce", "k_ipp_fold", "small_kernels"};
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
 struct VerifyState {          // what bp_rangeproof_verify_begin leaves for _finish
@@ -466,6 +467,164 @@ int bp_rangeproof_verify_batch_device(bp_ctx *c, bp_gens *gens, const uint8_t *t
     int rc = rp_verify_queue(c, gens, g, (uint32_t)count, (const uint8_t *)d_proofs, (const uint8_t *)d_commitments, transcript, seed, (uint32_t *)d_verdicts_u32);
     if (rc) return rc;
     if (h_batch_ok_pinned) CK(c, cudaMemcpyAsync(h_batch_ok_pinned, c->rp_batch_ok.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    return BP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- indexed MSMs and the IPP prover session
+static int check_scalars_canonical(const uint8_t *s, size_t n) {
+    for (size_t i = 0; i < n; i++) if (sc_geq_l(sc_load(s + 32 * i))) return BP_ERR_NONCANONICAL_SCALAR;
+    return BP_OK;
+}
+
+int bp_msm_indexed_batch(bp_ctx *c, bp_gens *gens, const uint8_t *scalars, const uint32_t *point_idx, const uint8_t *dyn_points, size_t n_dyn,
+                         const uint64_t *offsets, size_t n_msm, uint8_t *outs, uint8_t *status) {
+    if (!c || !offsets || !outs || n_msm == 0) return BP_ERR_INVALID_ARGUMENT;
+    size_t T = offsets[n_msm];
+    if (offsets[0] != 0 || T == 0 || T >= (1u << 31) || !scalars || !point_idx) return BP_ERR_INVALID_ARGUMENT;
+    CK(c, cudaSetDevice(c->device));
+    for (size_t t = 0; t < T; t++) {
+        uint32_t v = point_idx[t];
+        if (v & BP_POINT_DYNAMIC) { if ((v & 0x7fffffffu) >= n_dyn || !dyn_points) return BP_ERR_INVALID_ARGUMENT; }
+        else if (!gens || v >= gens->n_points) return BP_ERR_INVALID_ARGUMENT;
+    }
+    std::vector<uint32_t> off32(n_msm + 1);
+    for (size_t j = 0; j <= n_msm; j++) { if (j && offsets[j] < offsets[j - 1]) return BP_ERR_LENGTH_MISMATCH; off32[j] = (uint32_t)offsets[j]; }
+    cudaStream_t s = c->stream;
+    uint32_t M = (uint32_t)n_msm;
+    CK(c, c->in_scalars.ensure(T * 32)); CK(c, c->in_offsets.ensure((n_msm + 1) * 4)); CK(c, c->rp_pidx.ensure(T * 4));
+    CK(c, c->outs.ensure(n_msm * 32)); CK(c, c->flags.ensure(n_msm)); CK(c, c->msm_err.ensure((size_t)M * 4)); CK(c, c->results.ensure((size_t)M * sizeof(ge_ext)));
+    CK(c, cudaMemcpyAsync(c->in_scalars.p, scalars, T * 32, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->in_offsets.p, off32.data(), (n_msm + 1) * 4, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemcpyAsync(c->rp_pidx.p, point_idx, T * 4, cudaMemcpyHostToDevice, s));
+    CK(c, cudaMemsetAsync(c->msm_err.p, 0, (size_t)M * 4, s));
+    std::vector<uint8_t> dyn_ok;
+    if (n_dyn) {
+        CK(c, c->in_points.ensure(n_dyn * 32)); CK(c, c->niels.ensure(n_dyn * sizeof(ge_niels))); CK(c, c->ok.ensure(n_dyn));
+        CK(c, cudaMemcpyAsync(c->in_points.p, dyn_points, n_dyn * 32, cudaMemcpyHostToDevice, s));
+        LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n_dyn, 128), 128, 0, s>>>(c->in_points.as<uint8_t>(), n_dyn, c->niels.as<ge_niels>(), c->ok.as<uint8_t>()));
+        dyn_ok.resize(n_dyn);
+        CK(c, cudaMemcpyAsync(dyn_ok.data(), c->ok.p, n_dyn, cudaMemcpyDeviceToHost, s));
+    }
+    MsmArgs a{c->in_scalars.as<uint8_t>(), c->in_offsets.as<uint32_t>(), M, (uint32_t)T, c->rp_pidx.as<uint32_t>(), gens ? gens->d_table : nullptr, c->niels.as<ge_niels>(), c->msm_err.as<uint32_t>(), 0};
+    int rc = msm_core(c, a, c->results.as<ge_ext>());
+    if (rc) return rc;
+    LAUNCH(c, KID_COMPRESS, k_compress<<<blocks_for(M, 128), 128, 0, s>>>(c->results.as<ge_ext>(), M, c->outs.as<uint8_t>()));
+    LAUNCH(c, KID_SMALL, k_msm_status<<<blocks_for(M, 128), 128, 0, s>>>(c->msm_err.as<uint32_t>(), M, c->flags.as<uint8_t>()));
+    std::vector<uint8_t> st(n_msm);
+    CK(c, cudaMemcpyAsync(outs, c->outs.p, n_msm * 32, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaMemcpyAsync(st.data(), c->flags.p, n_msm, cudaMemcpyDeviceToHost, s));
+    CK(c, cudaStreamSynchronize(s));
+    // an undecodable caller-supplied point poisons the MSMs that use it (optional_multiscalar_mul -> None)
+    if (n_dyn)
+        for (size_t j = 0; j < n_msm; j++)
+            for (size_t t = offsets[j]; t < offsets[j + 1]; t++)
+                if ((point_idx[t] & BP_POINT_DYNAMIC) && !dyn_ok[point_idx[t] & 0x7fffffffu] && st[j] == BP_OK) st[j] = BP_ERR_INVALID_POINT;
+    if (status) memcpy(status, st.data(), n_msm);
+    return BP_OK;
+}
+
+}  // extern "C"
+
+struct bp_ipp {
+    bp_ctx *ctx = nullptr; uint32_t N = 0; ge_niels *pts = nullptr;     // [G (N) | H (N) | Q]
+    DevBuf scal, idx, offs;
+};
+
+extern "C" {
+
+static int ipp_alloc(bp_ctx *c, size_t N, bp_ipp **out) {
+    if (!c || !out || N == 0 || (N & (N - 1)) || N >= (1u << 24)) return BP_ERR_INVALID_ARGUMENT;      // power of two (inner_product_proof.rs:67)
+    CK(c, cudaSetDevice(c->device));
+    bp_ipp *s = new bp_ipp(); s->ctx = c; s->N = (uint32_t)N;
+    cudaError_t e = cudaMalloc((void **)&s->pts, (2 * N + 1) * sizeof(ge_niels));
+    if (e != cudaSuccess) { c->err = std::string("cudaMalloc(ipp): ") + cudaGetErrorString(e); delete s; return BP_ERR_CUDA; }
+    *out = s; return BP_OK;
+}
+int bp_ipp_begin(bp_ctx *c, bp_gens *gens, size_t n, size_t m, const uint8_t Q[32], bp_ipp **out) {
+    if (!gens || !Q || n == 0 || m == 0 || n > gens->cap || m > gens->parties) return BP_ERR_INVALID_ARGUMENT;
+    size_t N = n * m;
+    int rc = ipp_alloc(c, N, out); if (rc) return rc;
+    bp_ipp *s = *out;
+    std::vector<uint32_t> idx(2 * N);
+    for (size_t q = 0; q < N; q++) {          // BulletproofGens::G(n, m) / H(n, m) iterator order (generators.rs:207-259)
+        idx[q] = (uint32_t)(2 + (q / n) * gens->cap + (q % n));
+        idx[N + q] = (uint32_t)(2 + gens->parties * gens->cap + (q / n) * gens->cap + (q % n));
+    }
+    cudaStream_t st = c->stream;
+    CK(c, s->idx.ensure(2 * N * 4)); CK(c, c->in_points.ensure(32)); CK(c, c->ok.ensure(1));
+    CK(c, cudaMemcpyAsync(s->idx.p, idx.data(), 2 * N * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(c->in_points.p, Q, 32, cudaMemcpyHostToDevice, st));
+    LAUNCH(c, KID_SMALL, k_gather_niels<<<blocks_for(2 * N, 128), 128, 0, st>>>(gens->d_table, s->idx.as<uint32_t>(), (uint32_t)(2 * N), s->pts));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<1, 128, 0, st>>>(c->in_points.as<uint8_t>(), 1, s->pts + 2 * N, c->ok.as<uint8_t>()));
+    uint8_t ok = 0;
+    CK(c, cudaMemcpyAsync(&ok, c->ok.p, 1, cudaMemcpyDeviceToHost, st)); CK(c, cudaStreamSynchronize(st));
+    if (!ok) { cudaFree(s->pts); delete s; *out = nullptr; return BP_ERR_INVALID_POINT; }
+    return BP_OK;
+}
+int bp_ipp_begin_points(bp_ctx *c, const uint8_t *G, const uint8_t *H, size_t N, const uint8_t Q[32], bp_ipp **out) {
+    if (!G || !H || !Q) return BP_ERR_INVALID_ARGUMENT;
+    int rc = ipp_alloc(c, N, out); if (rc) return rc;
+    bp_ipp *s = *out; cudaStream_t st = c->stream;
+    size_t n_pts = 2 * N + 1;
+    CK(c, c->in_points.ensure(n_pts * 32)); CK(c, c->ok.ensure(n_pts));
+    CK(c, cudaMemcpyAsync(c->in_points.p, G, N * 32, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(c->in_points.as<uint8_t>() + N * 32, H, N * 32, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(c->in_points.as<uint8_t>() + 2 * N * 32, Q, 32, cudaMemcpyHostToDevice, st));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n_pts, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), n_pts, s->pts, c->ok.as<uint8_t>()));
+    std::vector<uint8_t> ok(n_pts);
+    CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, n_pts, cudaMemcpyDeviceToHost, st)); CK(c, cudaStreamSynchronize(st));
+    for (uint8_t v : ok) if (!v) { cudaFree(s->pts); delete s; *out = nullptr; return BP_ERR_INVALID_POINT; }
+    return BP_OK;
+}
+void bp_ipp_end(bp_ipp *s) { if (!s) return; cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); cudaFree(s->pts); s->scal.release(); s->idx.release(); s->offs.release(); delete s; }
+
+// one round's two MSMs: L = <sL[0..h), G_R> + <sL[h..2h), H_L> + sL[2h] Q ;  R = <sR[0..h), G_L> + <sR[h..2h), H_R> + sR[2h] Q
+// (inner_product_proof.rs:87-113,153-163); h = n_half = current length / 2
+int bp_ipp_lr(bp_ipp *s, size_t n_half, const uint8_t *scalars_L, const uint8_t *scalars_R, uint8_t L_out[32], uint8_t R_out[32]) {
+    if (!s || !scalars_L || !scalars_R || !L_out || !R_out || n_half == 0 || 2 * n_half > s->N) return BP_ERR_INVALID_ARGUMENT;
+    bp_ctx *c = s->ctx; CK(c, cudaSetDevice(c->device));
+    size_t h = n_half, per = 2 * h + 1, N = s->N;
+    if (check_scalars_canonical(scalars_L, per) || check_scalars_canonical(scalars_R, per)) return BP_ERR_NONCANONICAL_SCALAR;
+    std::vector<uint32_t> idx(2 * per), offs = {0, (uint32_t)per, (uint32_t)(2 * per)};
+    for (size_t i = 0; i < h; i++) {
+        idx[i] = BP_POINT_DYNAMIC | (uint32_t)(h + i);              // G_R
+        idx[h + i] = BP_POINT_DYNAMIC | (uint32_t)(N + i);          // H_L
+        idx[per + i] = BP_POINT_DYNAMIC | (uint32_t)i;              // G_L
+        idx[per + h + i] = BP_POINT_DYNAMIC | (uint32_t)(N + h + i);  // H_R
+    }
+    idx[2 * h] = idx[per + 2 * h] = BP_POINT_DYNAMIC | (uint32_t)(2 * N);   // Q
+    cudaStream_t st = c->stream;
+    CK(c, s->scal.ensure(2 * per * 32)); CK(c, s->idx.ensure(std::max<size_t>(2 * per, 2 * N) * 4)); CK(c, s->offs.ensure(16));
+    CK(c, c->results.ensure(2 * sizeof(ge_ext))); CK(c, c->outs.ensure(64));
+    CK(c, cudaMemcpyAsync(s->scal.p, scalars_L, per * 32, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(s->scal.as<uint8_t>() + per * 32, scalars_R, per * 32, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(s->idx.p, idx.data(), 2 * per * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaMemcpyAsync(s->offs.p, offs.data(), 12, cudaMemcpyHostToDevice, st));
+    MsmArgs a{s->scal.as<uint8_t>(), s->offs.as<uint32_t>(), 2, (uint32_t)(2 * per), s->idx.as<uint32_t>(), nullptr, s->pts, nullptr, 0};
+    int rc = msm_core(c, a, c->results.as<ge_ext>());
+    if (rc) return rc;
+    LAUNCH(c, KID_COMPRESS, k_compress<<<1, 128, 0, st>>>(c->results.as<ge_ext>(), 2, c->outs.as<uint8_t>()));
+    uint8_t lr[64];
+    CK(c, cudaMemcpyAsync(lr, c->outs.p, 64, cudaMemcpyDeviceToHost, st)); CK(c, cudaStreamSynchronize(st));
+    memcpy(L_out, lr, 32); memcpy(R_out, lr + 32, 32);
+    return BP_OK;
+}
+// G_L[i] = g_lo[i] G_L[i] + g_hi[i] G_R[i] ;  H_L[i] = h_lo[i] H_L[i] + h_hi[i] H_R[i]   (inner_product_proof.rs:124-135,174-179).
+// per_index = 1: n_half scalars in each array (first round, factors folded in); 0: one scalar each (u^-1, u / u, u^-1).
+int bp_ipp_fold(bp_ipp *s, size_t n_half, const uint8_t *g_lo, const uint8_t *g_hi, const uint8_t *h_lo, const uint8_t *h_hi, int per_index) {
+    if (!s || !g_lo || !g_hi || !h_lo || !h_hi || n_half == 0 || 2 * n_half > s->N) return BP_ERR_INVALID_ARGUMENT;
+    bp_ctx *c = s->ctx; CK(c, cudaSetDevice(c->device));
+    size_t cnt = per_index ? n_half : 1, h = n_half;
+    const uint8_t *arrs[4] = {g_lo, g_hi, h_lo, h_hi};
+    for (auto a : arrs) if (check_scalars_canonical(a, cnt)) return BP_ERR_NONCANONICAL_SCALAR;
+    cudaStream_t st = c->stream;
+    CK(c, s->scal.ensure(4 * cnt * 32));
+    for (int k = 0; k < 4; k++) CK(c, cudaMemcpyAsync(s->scal.as<uint8_t>() + (size_t)k * cnt * 32, arrs[k], cnt * 32, cudaMemcpyHostToDevice, st));
+    uint32_t stride = per_index ? 32 : 0;
+    const uint8_t *d = s->scal.as<uint8_t>();
+    LAUNCH(c, KID_IPP_FOLD, k_ipp_fold<<<blocks_for(h, 64), 64, 0, st>>>(s->pts, (uint32_t)h, d, d + cnt * 32, stride));
+    LAUNCH(c, KID_IPP_FOLD, k_ipp_fold<<<blocks_for(h, 64), 64, 0, st>>>(s->pts + s->N, (uint32_t)h, d + 2 * cnt * 32, d + 3 * cnt * 32, stride));
+    CK(c, cudaStreamSynchronize(st));          // the scalar staging buffer is reused by the next round
     return BP_OK;
 }
 

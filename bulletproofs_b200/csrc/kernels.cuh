@@ -244,6 +244,38 @@ __global__ void k_msm_combine(const ge_ext *__restrict__ window_sums, uint32_t n
     st_ext(results + m, acc);
 }
 
+// ------------------------------------------------------------------ K4: IPP generator fold
+// out[i] = s_lo[i] * P[i] + s_hi[i] * P[half + i], written back to P[i] in affine Niels form
+// (InnerProductProof::create's G/H fold, /root/reference/src/inner_product_proof.rs:127-134,177-178).
+// One thread per i: joint double-and-add over the two scalars (shared doublings), then one inversion
+// to renormalise so that the next round's MSMs keep using 7-multiplication mixed additions.
+// scalars: canonical 32-byte little-endian; stride 0 = the same pair for every i (later rounds).
+__global__ void __launch_bounds__(64) k_ipp_fold(ge_niels *__restrict__ P, uint32_t half, const uint8_t *__restrict__ s_lo, const uint8_t *__restrict__ s_hi, uint32_t stride) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= half) return;
+    uint8_t b1[32], b2[32]; ld32(b1, s_lo + (size_t)i * stride); ld32(b2, s_hi + (size_t)i * stride);
+    sc k1 = sc_load(b1), k2 = sc_load(b2);
+    ge_niels p1 = ldg_niels(P + i), p2 = ldg_niels(P + half + i);
+    ge_ext e12 = ge_madd(ge_from_niels(p1), p2);
+    fe zi = fe_invert(e12.Z);
+    ge_niels p12 = ge_to_niels_affine(fe_mul(e12.X, zi), fe_mul(e12.Y, zi));
+    ge_ext acc = ge_identity();
+#pragma unroll 1
+    for (int bit = 252; bit >= 0; bit--) {
+        acc = ge_dbl(acc);
+        uint32_t d = ((k1.v[bit >> 5] >> (bit & 31)) & 1u) | (((k2.v[bit >> 5] >> (bit & 31)) & 1u) << 1);
+        if (d) { ge_niels q = d == 1 ? p1 : (d == 2 ? p2 : p12); acc = ge_madd(acc, q); }
+    }
+    fe zf = fe_invert(acc.Z);
+    st_niels(P + i, ge_to_niels_affine(fe_mul(acc.X, zf), fe_mul(acc.Y, zf)));
+}
+// copy table entries (by index) into a contiguous device vector: G(n,m) / H(n,m) slices for the IPP prover
+__global__ void k_gather_niels(const ge_niels *__restrict__ table, const uint32_t *__restrict__ idx, uint32_t n, ge_niels *__restrict__ out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st_niels(out + i, ldg_niels(table + idx[i]));
+}
+
 // ------------------------------------------------------------------ range-proof batch verification kernels
 struct rp_geom { uint32_t n, m, k, N, D, S; uint32_t proof_len; };   // D = 4+2k+m dynamic terms, S = 2+2N static terms
 

@@ -82,6 +82,31 @@ int bp_msm_batch(bp_ctx *ctx, const uint8_t *scalars, const uint8_t *points, con
 int bp_msm_batch_device(bp_ctx *ctx, const void *d_scalars, const void *d_points, const void *d_offsets_u32,
                         size_t n_msm, size_t total_terms, void *d_outs, void *d_status);
 
+/* MSMs whose points are generator-table entries and/or caller-supplied compressed points:
+ * point_idx[t] < 2^31 selects table slot point_idx[t] of `gens` (layout of bp_gens_device_table: 0 = B_blinding,
+ * 1 = B, 2 + party*cap + i = G[party][i], 2 + parties*cap + party*cap + i = H[party][i]); point_idx[t] = 2^31 | j
+ * selects dyn_points[j].  This is how the prover-side constant-base call sites run without re-uploading the table:
+ * PedersenGens::commit (generators.rs:39-41), A and S (range_proof/party.rs:100-124), T_1/T_2 (party.rs:216-217),
+ * Q = w*B (dealer.rs:256), and the stand-alone IPP verification MSM (inner_product_proof.rs:308-319). */
+int bp_msm_indexed_batch(bp_ctx *ctx, bp_gens *gens, const uint8_t *scalars, const uint32_t *point_idx,
+                         const uint8_t *dyn_points, size_t n_dyn, const uint64_t *offsets, size_t n_msm,
+                         uint8_t *outs, uint8_t *status);
+
+/* ---- inner-product argument, prover side (InnerProductProof::create, inner_product_proof.rs:38-193) ---- */
+/* The generator vectors G, H (and Q) live on the device for the k rounds; the host keeps the transcript and
+ * the scalar vectors a, b and calls once per round for L,R and once for the fold. */
+typedef struct bp_ipp bp_ipp;
+/* G = bp_gens.G(n, m), H = bp_gens.H(n, m) (N = n*m points each), Q compressed */
+int bp_ipp_begin(bp_ctx *ctx, bp_gens *gens, size_t n, size_t m, const uint8_t Q[32], bp_ipp **out);
+/* arbitrary vectors: G, H = N compressed points each (the reference's Vec<RistrettoPoint> arguments) */
+int bp_ipp_begin_points(bp_ctx *ctx, const uint8_t *G, const uint8_t *H, size_t N, const uint8_t Q[32], bp_ipp **out);
+/* L = <sL[0..h), G_R> + <sL[h..2h), H_L> + sL[2h] Q,  R = <sR[0..h), G_L> + <sR[h..2h), H_R> + sR[2h] Q  (lines 87-113 / 153-163) */
+int bp_ipp_lr(bp_ipp *sess, size_t n_half, const uint8_t *scalars_L, const uint8_t *scalars_R, uint8_t L_out[32], uint8_t R_out[32]);
+/* G_L[i] = g_lo G_L[i] + g_hi G_R[i], H_L[i] = h_lo H_L[i] + h_hi H_R[i]  (lines 127-134 / 177-178);
+ * per_index = 1: n_half scalars per array (first round, factors folded in), 0: one scalar per array */
+int bp_ipp_fold(bp_ipp *sess, size_t n_half, const uint8_t *g_lo, const uint8_t *g_hi, const uint8_t *h_lo, const uint8_t *h_hi, int per_index);
+void bp_ipp_end(bp_ipp *sess);
+
 /* ---- generator tables ---------------------------------------------------------------------- */
 /* BulletproofGens::new(gens_capacity, party_capacity) + PedersenGens::default()
  * (generators.rs:44-53,157-204): SHAKE256 expansion on the host, Elligator maps and the

@@ -20,6 +20,7 @@ def built():
     b.build_oracle()
     b.build_emul()
     b.build_cuda()
+    b.build_host()
     return True
 
 

@@ -156,9 +156,9 @@ def main():
     table = torch.empty(table_bytes, dtype=torch.uint8, device="cuda")
     if rank == 0:
         gens0.table_export(table.data_ptr())
-    if world > 1:
-        dist.broadcast(table, src=0)
-        torch.cuda.synchronize()
+    from bulletproofs_b200.dist import broadcast_table
+    broadcast_table(table, src=0)                  # the path's only collective: one NCCL broadcast over NVLink
+    torch.cuda.synchronize()
     gens = [gens0]
     if rank != 0:
         gens0.table_import(table.data_ptr())

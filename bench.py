@@ -37,6 +37,24 @@ LABEL = b"AggregateRangeProofBenchmark"            # benches/range_proof.rs:34
 L2_BYTES = 126 * 1024 * 1024
 
 
+def effective_cores():
+    """host cores this process may actually use: min(affinity, cgroup cpu.max quota)"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture
+# profiles/r1_v2_ncu_full.md; the scratch arrays (sorted ids, buckets, contrib) make it larger than the algorithmic bytes
+NCU_TRAFFIC_BYTES = {"k_msm_accumulate": 3.62e6, "k_msm_reduce": 3.37e6, "k_msm_combine": 0.048e6, "k_rp_transcript": 1.05e6,
+                     "k_rp_scalars": 2.84e6, "k_rp_decompress": 0.825e6, "k_rp_static_reduce": 4.27e6}
+
+
 def make_workload(count, rank):
     """Synthetic input: `count` valid (64,1) proofs over uniform 64-bit values and uniform blindings.
     The proofs are produced by the CPU oracle's prover (test infrastructure used as a data generator only;
@@ -49,7 +67,7 @@ def make_workload(count, rank):
     values = [rnd.randrange(1 << N_BITS) for _ in range(count * M_PARTIES)]
     blind = b"".join(rnd.randrange(L_ORDER).to_bytes(32, "little") for _ in range(count * M_PARTIES))
     seeds = b"".join((rank * count + i).to_bytes(8, "little") + bytes(24) for i in range(count))
-    proofs, Vs = orc.prove_many(og, orc.transcript(LABEL), values, blind, N_BITS, M_PARTIES, seeds, nthreads=os.cpu_count() or 4)
+    proofs, Vs = orc.prove_many(og, orc.transcript(LABEL), values, blind, N_BITS, M_PARTIES, seeds, nthreads=effective_cores())
     return orc, og, proofs, Vs
 
 
@@ -91,7 +109,7 @@ def run_reference(args, rank, world):
     (oracle restatement, kind "port").  Rank 0 only."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = effective_cores()
     orc, og, proofs, Vs = make_workload(BATCH, 0)
     plen = len(proofs) // BATCH
     t = orc.transcript(LABEL)
@@ -114,7 +132,8 @@ def run_reference(args, rank, world):
     print(json.dumps({"impl": "reference", "metric": "64-bit rangeproof verifications/sec (batched)", "value": value, "unit": "proofs/s", "n_gpus": 0,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "u64 (51-bit limbs, CPU)", "data": "synthetic",
-                      "config": {"workload": f"batched verify of {BATCH}x 64-bit RangeProofs (m=1), sample {sample} proofs/step", "n": N_BITS, "m": M_PARTIES},
+                      "config": {"workload": f"batched verify of {BATCH}x 64-bit RangeProofs (m=1) per GPU", "n": N_BITS, "m": M_PARTIES, "batch": BATCH,
+                                 "reference_sample": f"{sample} proofs per step on {cores} host threads"},
                       "cpu_baseline": cpu, "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -124,7 +143,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--streams", type=int, default=8)
+    ap.add_argument("--streams", type=int, default=24)
     ap.add_argument("--threads", type=int, default=1, help="host threads issuing steps (each drives streams/threads contexts)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -278,7 +297,7 @@ def main():
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_TRAFFIC_BYTES.get(dom),
                 "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)",
                 "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": dom_ms, "kernel_share_of_step": prof[dom][0] / total_ms,
                 "note": "integer-pipe bound path: HBM fraction is reported as BASELINE.json asks; see profiles/ for IMAD issue utilisation",
@@ -293,7 +312,7 @@ def main():
            "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = effective_cores()
         t = orc.transcript(LABEL)
         done, t0 = 0, time.perf_counter()
         while time.perf_counter() - t0 < 12.0:

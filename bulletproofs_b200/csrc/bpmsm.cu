@@ -48,7 +48,7 @@ struct bp_ctx {
     std::string err; uint64_t launches = 0;
     bool prof_on = false; std::vector<ProfRec> prof;          // per-kernel CUDA-event timing (bp_prof_*)
     // MSM scratch
-    DevBuf in_scalars, in_points, in_offsets, niels, ok, msm_err, counts, starts, cursor, sorted, buckets, wsums, results, outs, flags;
+    DevBuf in_scalars, in_points, in_offsets, niels, ok, msm_err, counts, starts, cursor, order, sorted, buckets, wsums, results, outs, flags;
     // range-proof scratch
     DevBuf rp_chal, rp_tabs, pow2_tab, rp_proofs, rp_commit, rp_tstate, rp_seed, rp_contrib, rp_scalars, rp_status, rp_pidx, rp_offsets, rp_verdict, rp_batch_ok;
     DevBuf fb_scalars, fb_pidx, fb_offsets;
@@ -107,16 +107,20 @@ int msm_core(bp_ctx *ctx, const MsmArgs &a, ge_ext *d_results) {
     int W = msm_num_windows(c);
     uint32_t nb = 1u << (c - 1);
     size_t segs = (size_t)a.n_msm * W, n_buckets = segs * nb;
-    CK(ctx, ctx->counts.ensure(n_buckets * 4)); CK(ctx, ctx->starts.ensure(n_buckets * 4)); CK(ctx, ctx->cursor.ensure(n_buckets * 4));
+    // counts | size histogram | bin cursors share one allocation so a single memset clears them
+    CK(ctx, ctx->counts.ensure((n_buckets + 2 * MSM_SIZE_BINS) * 4)); CK(ctx, ctx->starts.ensure(n_buckets * 4)); CK(ctx, ctx->cursor.ensure(n_buckets * 4));
+    CK(ctx, ctx->order.ensure(n_buckets * 4));
+    uint32_t *size_hist = ctx->counts.as<uint32_t>() + n_buckets, *bin_cursor = size_hist + MSM_SIZE_BINS;
     CK(ctx, ctx->sorted.ensure((size_t)a.T * W * 4)); CK(ctx, ctx->buckets.ensure(n_buckets * sizeof(ge_ext))); CK(ctx, ctx->wsums.ensure(segs * sizeof(ge_ext)));
     cudaStream_t s = ctx->stream;
-    CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, n_buckets * 4, s));
+    CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, (n_buckets + 2 * MSM_SIZE_BINS) * 4, s));
     LAUNCH(ctx, KID_MSM_COUNT, k_msm_count<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->counts.as<uint32_t>(), a.d_err));
-    LAUNCH(ctx, KID_MSM_SCAN, k_msm_scan<<<(unsigned)segs, 256, 0, s>>>(ctx->counts.as<uint32_t>(), nb, ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>()));
+    LAUNCH(ctx, KID_MSM_SCAN, k_msm_scan<<<(unsigned)segs, 256, 0, s>>>(ctx->counts.as<uint32_t>(), nb, ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), size_hist));
+    LAUNCH(ctx, KID_MSM_SCAN, k_msm_order<<<blocks_for(n_buckets, 256), 256, 0, s>>>(ctx->counts.as<uint32_t>(), n_buckets, size_hist, bin_cursor, ctx->order.as<uint32_t>()));
     LAUNCH(ctx, KID_MSM_SCATTER, k_msm_scatter<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>()));
-    LAUNCH(ctx, KID_MSM_ACCUMULATE, k_msm_accumulate<<<blocks_for(n_buckets, 128), 128, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(), a.d_offsets, W, nb,
+    LAUNCH(ctx, KID_MSM_ACCUMULATE, k_msm_accumulate<<<blocks_for(n_buckets, 128), 128, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(), a.d_offsets, ctx->order.as<uint32_t>(), W, nb,
                                                                 n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>()));
-    unsigned rthreads = nb >= 256 ? 256 : (nb < 32 ? 32 : nb);
+    unsigned rthreads = nb >= 64 ? 64 : 32;      // two warps per segment: fewer scan/tree additions per useful bucket addition
     LAUNCH(ctx, KID_MSM_REDUCE, k_msm_reduce<<<(unsigned)segs, rthreads, 0, s>>>(ctx->buckets.as<ge_ext>(), nb, ctx->wsums.as<ge_ext>()));
     LAUNCH(ctx, KID_MSM_COMBINE, k_msm_combine<<<blocks_for(a.n_msm, 32), 32, 0, s>>>(ctx->wsums.as<ge_ext>(), a.n_msm, c, W, d_results));
     return BP_OK;
@@ -179,7 +183,7 @@ void bp_ctx_destroy(bp_ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf *bufs[] = {&c->in_scalars, &c->in_points, &c->in_offsets, &c->niels, &c->ok, &c->msm_err, &c->counts, &c->starts, &c->cursor, &c->sorted, &c->buckets,
+    DevBuf *bufs[] = {&c->in_scalars, &c->in_points, &c->in_offsets, &c->niels, &c->ok, &c->msm_err, &c->counts, &c->starts, &c->cursor, &c->order, &c->sorted, &c->buckets,
                       &c->wsums, &c->results, &c->outs, &c->flags, &c->rp_chal, &c->rp_tabs, &c->pow2_tab, &c->rp_proofs, &c->rp_commit, &c->rp_tstate, &c->rp_seed, &c->rp_contrib, &c->rp_scalars,
                       &c->rp_status, &c->rp_pidx, &c->rp_offsets, &c->rp_verdict, &c->rp_batch_ok, &c->fb_scalars, &c->fb_pidx, &c->fb_offsets};
     for (DevBuf *b : bufs) b->release();

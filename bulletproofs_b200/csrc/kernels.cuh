@@ -132,8 +132,13 @@ __global__ void __launch_bounds__(256) k_msm_count(const uint8_t *__restrict__ s
     }
 }
 // pass 2: per-segment exclusive scan of the bucket counts (block per segment); cursor starts as a copy
-__global__ void __launch_bounds__(256) k_msm_scan(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t *__restrict__ starts, uint32_t *__restrict__ cursor) {
+#define MSM_SIZE_BINS 256        // bucket sizes are clamped to MSM_SIZE_BINS-1 for the load-balancing order
+__global__ void __launch_bounds__(256) k_msm_scan(const uint32_t *__restrict__ counts, uint32_t nb, uint32_t *__restrict__ starts, uint32_t *__restrict__ cursor,
+                                                  uint32_t *__restrict__ size_hist) {
     __shared__ uint32_t warp_sums[8];
+    __shared__ uint32_t hist[MSM_SIZE_BINS];
+    for (uint32_t i = threadIdx.x; i < MSM_SIZE_BINS; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
     size_t seg = blockIdx.x;
     const uint32_t *cnt = counts + seg * nb; uint32_t *st = starts + seg * nb, *cu = cursor + seg * nb;
     uint32_t per = (nb + blockDim.x - 1) / blockDim.x;
@@ -148,7 +153,29 @@ __global__ void __launch_bounds__(256) k_msm_scan(const uint32_t *__restrict__ c
     uint32_t base = 0;
     for (uint32_t k = 0; k < wid; k++) base += warp_sums[k];
     uint32_t run = base + v - local;
-    for (uint32_t i = lo; i < hi; i++) { st[i] = run; cu[i] = run; run += cnt[i]; }
+    for (uint32_t i = lo; i < hi; i++) { uint32_t c_ = cnt[i]; st[i] = run; cu[i] = run; run += c_; atomicAdd(&hist[MSM_SIZE_BINS - 1 - min(c_, (uint32_t)MSM_SIZE_BINS - 1)], 1u); }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < MSM_SIZE_BINS; i += blockDim.x) if (hist[i]) atomicAdd(size_hist + i, hist[i]);
+}
+// load-balancing order: bucket ids sorted by decreasing size (counting sort over the size histogram), so that the 32
+// buckets a warp accumulates have (nearly) equal lengths and the longest buckets start first
+__global__ void __launch_bounds__(256) k_msm_order(const uint32_t *__restrict__ counts, size_t n_buckets, const uint32_t *__restrict__ size_hist,
+                                                   uint32_t *__restrict__ bin_cursor, uint32_t *__restrict__ order) {
+    __shared__ uint32_t base[MSM_SIZE_BINS];
+    __shared__ uint32_t wsum[8];
+    {   // exclusive scan of the 256-bin histogram, redundantly per block
+        uint32_t v = size_hist[threadIdx.x], lane = threadIdx.x & 31, wid = threadIdx.x >> 5, x = v;
+        for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += o; }
+        if (lane == 31) wsum[wid] = x;
+        __syncthreads();
+        uint32_t b = 0; for (uint32_t k = 0; k < wid; k++) b += wsum[k];
+        base[threadIdx.x] = b + x - v;
+        __syncthreads();
+    }
+    size_t gb = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gb >= n_buckets) return;
+    uint32_t bin = MSM_SIZE_BINS - 1 - min(counts[gb], (uint32_t)MSM_SIZE_BINS - 1);
+    order[base[bin] + atomicAdd(bin_cursor + bin, 1u)] = (uint32_t)gb;
 }
 // pass 3: scatter term ids (sign in bit 31) into their bucket's slice
 __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *__restrict__ scalars, const uint32_t *__restrict__ offsets, uint32_t n_msm, uint32_t T,
@@ -172,11 +199,12 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *__restrict__
 }
 // pass 4: bucket accumulation, one thread per bucket: sum of +-points listed in its slice (mixed additions)
 __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
-                                                        const uint32_t *__restrict__ offsets, int W, uint32_t nb, size_t n_buckets,
+                                                        const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, int W, uint32_t nb, size_t n_buckets,
                                                         const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,
                                                         ge_ext *__restrict__ buckets) {
-    size_t gb = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gb >= n_buckets) return;
+    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= n_buckets) return;
+    size_t gb = order[tid];
     size_t seg = gb / nb; uint32_t msm = (uint32_t)(seg / W), w = (uint32_t)(seg % W);
     uint32_t o0 = __ldg(offsets + msm), len = __ldg(offsets + msm + 1) - o0;
     const uint32_t *slice = sorted + (size_t)W * o0 + (size_t)w * len;

@@ -199,9 +199,11 @@ static int ipp_verification_scalars(const ipp_view *p, size_t n, merlin *t, sc *
         if (t_validate_and_append_point(t, "R", p->LR + 64 * i + 32)) return ORC_VERIFICATION_ERROR;
         t_challenge_scalar(t, "u", &ch[i]);
     }
-    /* batch_invert: each inverse + product of all inverses (:226-227) */
-    sc_one(&allinv);
-    for (int i = 0; i < lg_n; i++) { sc_invert(&chi[i], &ch[i]); sc_mul(&allinv, &allinv, &chi[i]); }
+    /* Scalar::batch_invert: each inverse + product of all inverses (:226-227), one field inversion (Montgomery's trick) */
+    { sc pre[33], inv; sc_one(&pre[0]);
+      for (int i = 0; i < lg_n; i++) sc_mul(&pre[i + 1], &pre[i], &ch[i]);
+      sc_invert(&inv, &pre[lg_n]); allinv = inv;
+      for (int i = lg_n - 1; i >= 0; i--) { sc_mul(&chi[i], &inv, &pre[i]); sc_mul(&inv, &inv, &ch[i]); } }
     for (int i = 0; i < lg_n; i++) { sc_mul(&u_sq[i], &ch[i], &ch[i]); sc_mul(&u_inv_sq[i], &chi[i], &chi[i]); }
     s[0] = allinv;
     for (size_t i = 1; i < n; i++) {

@@ -68,7 +68,24 @@ static inline void fe_mul(fe *h, const fe *f, const fe *g) {
     h->v[0] = h0; h->v[1] = h1; h->v[2] = h2; h->v[3] = h3; h->v[4] = h4;
 }
 
-static inline void fe_sq(fe *h, const fe *f) { fe_mul(h, f, f); }
+static inline void fe_sq(fe *h, const fe *f) {       /* 15 limb products instead of 25 */
+    uint64_t f0 = f->v[0], f1 = f->v[1], f2 = f->v[2], f3 = f->v[3], f4 = f->v[4];
+    uint64_t f0_2 = 2 * f0, f1_2 = 2 * f1, f3_19 = 19 * f3, f4_19 = 19 * f4;
+    u128 r0 = (u128)f0 * f0 + (u128)(2 * f1) * f4_19 + (u128)(2 * f2) * f3_19;
+    u128 r1 = (u128)f0_2 * f1 + (u128)(2 * f2) * f4_19 + (u128)f3 * f3_19;
+    u128 r2 = (u128)f0_2 * f2 + (u128)f1 * f1 + (u128)(2 * f3) * f4_19;
+    u128 r3 = (u128)f0_2 * f3 + (u128)f1_2 * f2 + (u128)f4 * f4_19;
+    u128 r4 = (u128)f0_2 * f4 + (u128)f1_2 * f3 + (u128)f2 * f2;
+    uint64_t c;
+    r1 += (uint64_t)(r0 >> 51); uint64_t h0 = (uint64_t)r0 & FE_MASK51;
+    r2 += (uint64_t)(r1 >> 51); uint64_t h1 = (uint64_t)r1 & FE_MASK51;
+    r3 += (uint64_t)(r2 >> 51); uint64_t h2 = (uint64_t)r2 & FE_MASK51;
+    r4 += (uint64_t)(r3 >> 51); uint64_t h3 = (uint64_t)r3 & FE_MASK51;
+    c = (uint64_t)(r4 >> 51);   uint64_t h4 = (uint64_t)r4 & FE_MASK51;
+    h0 += c * 19;
+    c = h0 >> 51; h0 &= FE_MASK51; h1 += c;
+    h->v[0] = h0; h->v[1] = h1; h->v[2] = h2; h->v[3] = h3; h->v[4] = h4;
+}
 
 static inline void fe_sqn(fe *h, const fe *f, int n) {
     fe_sq(h, f);

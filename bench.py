@@ -140,8 +140,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=1000)
+    ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--streams", type=int, default=24)
     ap.add_argument("--threads", type=int, default=1, help="host threads issuing steps (each drives streams/threads contexts)")

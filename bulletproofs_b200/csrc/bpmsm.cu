@@ -55,6 +55,7 @@ struct bp_ctx {
     uint32_t *h_verdict = nullptr; size_t h_verdict_cap = 0;       // pinned
     uint32_t *h_flag = nullptr;                                      // pinned, 4 words
     VerifyState vs;
+    size_t pidx_key[5] = {0, 0, 0, 0, 0};                           // geometry the cached rp_pidx map was built for
 };
 
 struct bp_gens {
@@ -355,7 +356,7 @@ static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t 
     uint8_t seedbuf[32];
     if (seed) memcpy(seedbuf, seed, 32);
     else if (getrandom(seedbuf, 32, 0) != 32) { c->err = "getrandom failed"; return BP_ERR_CUDA; }
-    CK(c, c->rp_tstate.ensure(256)); CK(c, c->rp_seed.ensure(32));
+    CK(c, c->rp_tstate.ensure(512));
     CK(c, c->rp_contrib.ensure((size_t)count * g.S * sizeof(sc))); CK(c, c->rp_scalars.ensure((size_t)T * 32));
     CK(c, c->rp_status.ensure((size_t)count * 4)); CK(c, c->niels.ensure((size_t)count * g.D * sizeof(ge_niels)));
     CK(c, c->rp_pidx.ensure((size_t)T * 4)); CK(c, c->rp_offsets.ensure(8)); CK(c, c->results.ensure(sizeof(ge_ext)));
@@ -372,10 +373,11 @@ static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t 
     memcpy(stage, h_transcript, BP_TRANSCRIPT_BYTES); memcpy(stage + 256, seedbuf, 32);
     uint32_t offs[2] = {0, T}; memcpy(stage + 320, offs, 8);
     uint32_t one = 1; memcpy(stage + 336, &one, 4);
-    CK(c, cudaMemcpyAsync(c->rp_tstate.p, stage, BP_TRANSCRIPT_BYTES, cudaMemcpyHostToDevice, s));
-    CK(c, cudaMemcpyAsync(c->rp_seed.p, stage + 256, 32, cudaMemcpyHostToDevice, s));
-    CK(c, cudaMemcpyAsync(c->rp_offsets.p, stage + 320, 8, cudaMemcpyHostToDevice, s));
-    CK(c, cudaMemcpyAsync(c->rp_batch_ok.p, stage + 336, 4, cudaMemcpyHostToDevice, s));
+    // one 512-byte parameter block: transcript (0..202) | seed (256..287) | MSM offsets (320..327) | batch flag (336..339)
+    CK(c, cudaMemcpyAsync(c->rp_tstate.p, stage, 512, cudaMemcpyHostToDevice, s));
+    uint8_t *d_par = c->rp_tstate.as<uint8_t>();
+    const uint8_t *d_tstate = d_par, *d_seed = d_par + 256;
+    uint32_t *d_offsets = reinterpret_cast<uint32_t *>(d_par + 320), *d_batch_ok = reinterpret_cast<uint32_t *>(d_par + 336);
 
     uint8_t *d_scal = c->rp_scalars.as<uint8_t>();
     CK(c, c->rp_chal.ensure((size_t)count * sizeof(rp_head))); CK(c, c->rp_tabs.ensure((size_t)count * rp_tab_size(g.k, g.m) * sizeof(sc)));
@@ -385,17 +387,21 @@ static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t 
         CK(c, c->pow2_tab.ensure(64 * sizeof(sc)));
         CK(c, cudaMemcpyAsync(c->pow2_tab.p, tab.data(), 64 * sizeof(sc), cudaMemcpyHostToDevice, s)); CK(c, cudaStreamSynchronize(s));
     }
-    LAUNCH(c, KID_RP_TRANSCRIPT, k_rp_transcript<<<blocks_for(count, RP_TR_THREADS), RP_TR_THREADS, 0, s>>>(d_proofs, d_commit, g, c->rp_tstate.as<uint8_t>(), c->rp_seed.as<uint8_t>(), count,
+    LAUNCH(c, KID_RP_TRANSCRIPT, k_rp_transcript<<<blocks_for(count, RP_TR_THREADS), RP_TR_THREADS, 0, s>>>(d_proofs, d_commit, g, d_tstate, d_seed, count,
                                                                                                            c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(), c->rp_status.as<uint32_t>()));
     LAUNCH(c, KID_RP_SCALARS, k_rp_scalars<<<blocks_for((size_t)count * (g.N + g.D), 128), 128, 0, s>>>(g, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(), c->pow2_tab.as<sc>(), count, c->rp_contrib.as<sc>(), d_scal + (size_t)g.S * 32));
     LAUNCH(c, KID_RP_DECOMPRESS, k_rp_decompress<<<blocks_for((size_t)count * g.D, 128), 128, 0, s>>>(d_proofs, d_commit, g, count, c->niels.as<ge_niels>(), c->rp_status.as<uint32_t>()));
     LAUNCH(c, KID_RP_STATIC_REDUCE, k_rp_static_reduce<<<g.S, 128, 0, s>>>(c->rp_contrib.as<sc>(), g.S, count, d_scal));
-    LAUNCH(c, KID_SMALL, k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 0, c->rp_pidx.as<uint32_t>()));
-    MsmArgs a{d_scal, c->rp_offsets.as<uint32_t>(), 1, T, c->rp_pidx.as<uint32_t>(), gens->d_table, c->niels.as<ge_niels>(), nullptr, 0};
+    if (c->pidx_key[0] != g.n || c->pidx_key[1] != g.m || c->pidx_key[2] != count || c->pidx_key[3] != gens->cap || c->pidx_key[4] != gens->parties) {
+        // term -> point map of the combined MSM: depends only on the geometry, rebuilt when it changes
+        LAUNCH(c, KID_SMALL, k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 0, c->rp_pidx.as<uint32_t>()));
+        c->pidx_key[0] = g.n; c->pidx_key[1] = g.m; c->pidx_key[2] = count; c->pidx_key[3] = gens->cap; c->pidx_key[4] = gens->parties;
+    }
+    MsmArgs a{d_scal, d_offsets, 1, T, c->rp_pidx.as<uint32_t>(), gens->d_table, c->niels.as<ge_niels>(), nullptr, 0};
     int rc = msm_core(c, a, c->results.as<ge_ext>());
     if (rc) return rc;
     LAUNCH(c, KID_SMALL, k_is_identity<<<1, 32, 0, s>>>(c->results.as<ge_ext>(), 1, c->flags.as<uint32_t>()));
-    LAUNCH(c, KID_SMALL, k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 0, count, d_verdict, c->rp_batch_ok.as<uint32_t>()));
+    LAUNCH(c, KID_SMALL, k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 0, count, d_verdict, d_batch_ok));
     return BP_OK;
 }
 
@@ -413,7 +419,7 @@ static int rp_verify_fallback(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32
     int rc = msm_core(c, a, c->results.as<ge_ext>());
     if (rc) return rc;
     LAUNCH(c, KID_SMALL, k_is_identity<<<blocks_for(count, 128), 128, 0, s>>>(c->results.as<ge_ext>(), count, c->flags.as<uint32_t>()));
-    LAUNCH(c, KID_SMALL, k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 1, count, d_verdict, c->rp_batch_ok.as<uint32_t>()));
+    LAUNCH(c, KID_SMALL, k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 1, count, d_verdict, reinterpret_cast<uint32_t *>(c->rp_tstate.as<uint8_t>() + 336)));
     return BP_OK;
 }
 
@@ -470,7 +476,7 @@ int bp_rangeproof_verify_batch_device(bp_ctx *c, bp_gens *gens, const uint8_t *t
     if ((size_t)g.S + count * g.D >= (1u << 31)) return BP_ERR_INVALID_ARGUMENT;
     int rc = rp_verify_queue(c, gens, g, (uint32_t)count, (const uint8_t *)d_proofs, (const uint8_t *)d_commitments, transcript, seed, (uint32_t *)d_verdicts_u32);
     if (rc) return rc;
-    if (h_batch_ok_pinned) CK(c, cudaMemcpyAsync(h_batch_ok_pinned, c->rp_batch_ok.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    if (h_batch_ok_pinned) CK(c, cudaMemcpyAsync(h_batch_ok_pinned, c->rp_tstate.as<uint8_t>() + 336, 4, cudaMemcpyDeviceToHost, c->stream));
     return BP_OK;
 }
 

@@ -101,8 +101,37 @@ def host_lib():
         H.bph_ipp_create.argtypes = [_vp, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _sz, _u8p]
         H.bph_ipp_verify.restype = _int
         H.bph_ipp_verify.argtypes = [_vp, _u8p, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _sz]
+        H.bph_r1cs_prove.restype = _int
+        H.bph_r1cs_prove.argtypes = [_vp, _vp, _sz, _sz, _u8p, _int, _u8p, _u8p, _sz, _c.c_uint64, _c.c_uint64, _u8p, _u8p, _c.POINTER(_sz), _u8p]
+        H.bph_r1cs_verify.restype = _int
+        H.bph_r1cs_verify.argtypes = [_vp, _vp, _sz, _sz, _u8p, _int, _u8p, _sz, _c.c_uint64, _u8p, _sz, _u8p]
         _hlib = H
     return _hlib
+
+
+GADGET_SHUFFLE, GADGET_EXAMPLE, GADGET_RANGE = 0, 1, 2
+
+
+def r1cs_prove(ctx, gens, transcript, gadget: int, values, blindings: bytes, param: int = 0, aux: int = 0, ext_seed: bytes = bytes(32)):
+    """r1cs::Prover::{new, commit.., prove} with one of the reference's gadgets (shuffle: values = inputs then outputs;
+    example: a1,a2,b1,b2,c1 with param = c2; range: one value with param = n bits, aux = the value).  Returns
+    (status, R1CSProof::to_bytes(), commitments); ext_seed seeds the external RNG that finalises the TranscriptRng."""
+    m = len(values)
+    vals = b"".join(int(v).to_bytes(32, "little") for v in values)
+    proof = ctypes.create_string_buffer(1 + 32 * 14 + 32 * (2 * 32 + 2))
+    n = _sz()
+    V = ctypes.create_string_buffer(32 * max(m, 1))
+    rc = host_lib().bph_r1cs_prove(ctx._h, gens._h, gens.gens_capacity, gens.party_capacity, transcript.state, gadget, vals, blindings, m, param, aux, ext_seed, proof, ctypes.byref(n), V)
+    if rc < 0:
+        raise BpError(rc, lib().bp_last_error(ctx._h).decode())
+    return rc, proof.raw[:n.value], V.raw[:32 * m]
+
+
+def r1cs_verify(ctx, gens, transcript, gadget: int, commitments: bytes, proof: bytes, param: int = 0, ext_seed: bytes = bytes(32)) -> int:
+    rc = host_lib().bph_r1cs_verify(ctx._h, gens._h, gens.gens_capacity, gens.party_capacity, transcript.to_bytes(), gadget, commitments, len(commitments) // 32, param, proof, len(proof), ext_seed)
+    if rc < 0:
+        raise BpError(rc, lib().bp_last_error(ctx._h).decode())
+    return rc
 
 
 class Transcript:

@@ -86,6 +86,9 @@ BP_HDN void strobe_absorb(merlin_t &m, const uint8_t *d, uint32_t n) {
 BP_HDN void strobe_squeeze(merlin_t &m, uint8_t *d, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) { d[i] = m.st[m.pos]; m.st[m.pos] = 0; if (++m.pos == BP_STROBE_R) strobe_run_f(m); }
 }
+BP_HDN void strobe_overwrite(merlin_t &m, const uint8_t *d, uint32_t n) {      // KEY operation (TranscriptRng rekeying)
+    for (uint32_t i = 0; i < n; i++) { m.st[m.pos] = d[i]; if (++m.pos == BP_STROBE_R) strobe_run_f(m); }
+}
 BP_HD void strobe_begin_op(merlin_t &m, uint8_t flags) {
     uint8_t hdr[2] = { (uint8_t)m.pos_begin, flags };
     m.pos_begin = m.pos + 1; m.cur_flags = flags;

@@ -494,6 +494,40 @@ int orc_ipp_verify(uint8_t *transcript_state, size_t n, const uint8_t *Gf, const
     free(gf); free(hf); free(g); free(h); return rc;
 }
 
+/* ------------------------------------------------------------------ R1CS (prover.rs / verifier.rs) with three gadgets */
+#include "r1cs.h"
+
+static int r1cs_build(r1_cs *cs, int gadget, size_t m, uint64_t param, uint64_t aux, r1_var *vars, shuffle_ctx *sctx) {
+    if (gadget == 0) {                      /* shuffle: inputs then outputs (benches/r1cs.rs:98-120) */
+        if (m < 2 || m % 2) return ORC_FORMAT_ERROR;
+        sctx->k = m / 2; sctx->x = vars; sctx->y = vars + m / 2; shuffle_gadget(cs, sctx);
+    } else if (gadget == 1) { if (m != 5) return ORC_FORMAT_ERROR; example_gadget(cs, vars, param); }
+    else if (gadget == 2) { if (m != 1 || param > 64) return ORC_FORMAT_ERROR; range_gadget(cs, vars[0], aux, (size_t)param); }
+    else return ORC_FORMAT_ERROR;
+    return ORC_OK;
+}
+int orc_r1cs_prove(void *gens, const uint8_t *tstate, int gadget, const uint8_t *values, const uint8_t *blindings, size_t m, uint64_t param, uint64_t aux,
+                   const uint8_t ext_seed[32], uint8_t *proof_out, size_t *proof_len, uint8_t *commitments_out) {
+    merlin t; memcpy(&t, tstate, sizeof t);
+    chacha_rng ext; chacha_seed(&ext, ext_seed);
+    r1_cs cs; cs_init(&cs, 1, &t, default_pc());
+    r1_var *vars = malloc(sizeof(r1_var) * (m ? m : 1)); shuffle_ctx sctx;
+    for (size_t i = 0; i < m; i++) { sc v, b; sc_from_bytes_mod_order(&v, values + 32 * i); sc_from_bytes_mod_order(&b, blindings + 32 * i); vars[i] = cs_commit(&cs, &v, &b, NULL, commitments_out + 32 * i); }
+    int rc = r1cs_build(&cs, gadget, m, param, aux, vars, &sctx);
+    if (!rc) rc = r1cs_prove(&cs, gens, &ext, proof_out, proof_len);
+    cs_free(&cs); free(vars); return rc;
+}
+int orc_r1cs_verify(void *gens, const uint8_t *tstate, int gadget, const uint8_t *commitments, size_t m, uint64_t param, const uint8_t *proof, size_t len, const uint8_t ext_seed[32]) {
+    merlin t; memcpy(&t, tstate, sizeof t);
+    chacha_rng ext; chacha_seed(&ext, ext_seed);
+    r1_cs cs; cs_init(&cs, 0, &t, default_pc());
+    r1_var *vars = malloc(sizeof(r1_var) * (m ? m : 1)); shuffle_ctx sctx;
+    for (size_t i = 0; i < m; i++) vars[i] = cs_commit(&cs, NULL, NULL, commitments + 32 * i, NULL);
+    int rc = r1cs_build(&cs, gadget, m, param, 0, vars, &sctx);
+    if (!rc) rc = r1cs_verify(&cs, gens, proof, len, &ext);
+    cs_free(&cs); free(vars); return rc;
+}
+
 /* ------------------------------------------------------------------ multi-threaded batch drivers
  * (CPU baseline: independent proofs, one per task — the reference has no batch verifier, so this
  *  is "verify_multiple per proof" on all host cores) */

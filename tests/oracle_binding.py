@@ -37,6 +37,8 @@ class Oracle:
         L.orc_shake256.argtypes = [_p, _sz, _p, _sz]
         L.orc_ipp_create.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]
         L.orc_ipp_verify.argtypes = [_p, _sz, _p, _p, _p, _p, _p, _p, _p, _sz]
+        L.orc_r1cs_prove.argtypes = [_vp, _p, ctypes.c_int, _p, _p, _sz, ctypes.c_uint64, ctypes.c_uint64, _p, _p, ctypes.POINTER(_sz), _p]
+        L.orc_r1cs_verify.argtypes = [_vp, _p, ctypes.c_int, _p, _sz, ctypes.c_uint64, _p, _sz, _p]
         L.orc_init()
         assert L.orc_selfcheck() == 0
         self.tsize = L.orc_transcript_size()
@@ -150,6 +152,16 @@ class Oracle:
         o = ctypes.create_string_buffer(64)
         self.L.orc_sha3_512(data, len(data), o)
         return o.raw
+
+    # R1CS (gadget 0 shuffle, 1 example, 2 range)
+    def r1cs_prove(self, g, tstate, gadget, values, blindings, param=0, aux=0, ext_seed=bytes(32)):
+        m = len(values)
+        out = ctypes.create_string_buffer(1 + 32 * 14 + 32 * (2 * 32 + 2)); n = _sz(); V = ctypes.create_string_buffer(32 * max(m, 1))
+        rc = self.L.orc_r1cs_prove(g, tstate, gadget, b"".join(int(v).to_bytes(32, "little") for v in values), blindings, m, param, aux, ext_seed, out, ctypes.byref(n), V)
+        return rc, out.raw[:n.value], V.raw[:32 * m]
+
+    def r1cs_verify(self, g, tstate, gadget, commitments, proof, param=0, ext_seed=bytes(32)):
+        return self.L.orc_r1cs_verify(g, tstate, gadget, commitments, len(commitments) // 32, param, proof, len(proof), ext_seed)
 
     def ipp_create(self, tstate, Q, Gf, Hf, G, H, a, b, n):
         st = ctypes.create_string_buffer(tstate, 256)

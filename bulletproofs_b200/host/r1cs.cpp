@@ -91,6 +91,22 @@ std::pair<CompressedRistretto, Variable> Prover::commit(const Scalar &v, const S
     t_.append_point("V", V);
     return {V, Variable{VarKind::Committed, i}};
 }
+std::vector<std::pair<CompressedRistretto, Variable>> Prover::commit_vec(const std::vector<Scalar> &v, const std::vector<Scalar> &v_blinding) {
+    if (v.size() != v_blinding.size()) throw std::invalid_argument("commit_vec: lengths differ");
+    size_t m = v.size();
+    std::vector<std::pair<CompressedRistretto, Variable>> out(m);
+    if (m == 0) return out;
+    std::vector<Scalar> sc(2 * m); std::vector<uint32_t> idx(2 * m); std::vector<uint64_t> off(m + 1); std::vector<uint8_t> outs(32 * m), st(m);
+    for (size_t i = 0; i < m; i++) { sc[2 * i] = v[i]; sc[2 * i + 1] = v_blinding[i]; idx[2 * i] = gens_.slot_B(); idx[2 * i + 1] = gens_.slot_B_blinding(); off[i] = 2 * i; }
+    off[m] = 2 * m;
+    check(bp_msm_indexed_batch(dev_.ctx, gens_.handle, pack(sc).data(), idx.data(), nullptr, 0, off.data(), m, outs.data(), st.data()), dev_.ctx, "commit_vec");
+    for (size_t i = 0; i < m; i++) {
+        size_t j = v_.size(); v_.push_back(v[i]); v_blinding_.push_back(v_blinding[i]);
+        memcpy(out[i].first.data(), outs.data() + 32 * i, 32); out[i].second = Variable{VarKind::Committed, j};
+        t_.append_point("V", out[i].first);
+    }
+    return out;
+}
 Scalar Prover::eval(const LinearCombination &lc) const {
     Scalar acc = Scalar::zero();
     for (const auto &term : lc.terms) {
@@ -363,11 +379,10 @@ int bph_r1cs_prove(bp_ctx *ctx, bp_gens *gens, size_t gens_capacity, size_t part
     try {
         Device dev(ctx); BulletproofGens g{gens, gens_capacity, party_capacity}; Transcript t(transcript); ChaChaRng ext(ext_seed);
         Prover prover(dev, g, t);
-        std::vector<Variable> vars;
-        for (size_t i = 0; i < m; i++) {
-            Scalar v, b; if (!Scalar::from_canonical_bytes(values + 32 * i, v) || !Scalar::from_canonical_bytes(blindings + 32 * i, b)) return -3;
-            auto cv = prover.commit(v, b); memcpy(commitments_out + 32 * i, cv.first.data(), 32); vars.push_back(cv.second);
-        }
+        std::vector<Variable> vars; std::vector<Scalar> vs(m), bs(m);
+        for (size_t i = 0; i < m; i++) if (!Scalar::from_canonical_bytes(values + 32 * i, vs[i]) || !Scalar::from_canonical_bytes(blindings + 32 * i, bs[i])) return -3;
+        auto cvs = prover.commit_vec(vs, bs);
+        for (size_t i = 0; i < m; i++) { memcpy(commitments_out + 32 * i, cvs[i].first.data(), 32); vars.push_back(cvs[i].second); }
         R1CSError e = build_gadget(prover, gadget, vars, param, &aux); if (e != R1CSError::Ok) return (int)e;
         R1CSProof proof; e = prover.prove(ext, proof); if (e != R1CSError::Ok) return (int)e;
         std::vector<uint8_t> bytes = proof.to_bytes(); memcpy(proof_out, bytes.data(), bytes.size()); *proof_len = bytes.size();

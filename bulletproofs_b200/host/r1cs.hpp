@@ -76,6 +76,9 @@ class Prover : public ConstraintSystem {
 public:
     Prover(Device &dev, const BulletproofGens &gens, Transcript &t);                         // prover.rs:242-258 (pc_gens = the table's B, B~)
     std::pair<CompressedRistretto, Variable> commit(const Scalar &v, const Scalar &v_blinding);   // prover.rs:278-288
+    // the same as calling commit() for each pair in order (identical transcript and commitments), but all Pedersen
+    // commitments are computed by one batched GPU call instead of one launch sequence per variable
+    std::vector<std::pair<CompressedRistretto, Variable>> commit_vec(const std::vector<Scalar> &v, const std::vector<Scalar> &v_blinding);
     R1CSError prove(Rng &external_rng, R1CSProof &out);                                      // prover.rs:380-698
     Transcript &transcript() override { return t_; }
     Multiplier multiply(LinearCombination left, LinearCombination right) override;

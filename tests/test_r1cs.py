@@ -112,3 +112,33 @@ def test_gpu_example_and_range_gadgets_match_oracle(gpu_ctx, orc):
             got = bp.r1cs_verify(gpu_ctx, gens, bp.Transcript(b"RangeProofTest"), bp.GADGET_RANGE, V, proof, param=n)
             assert (got == 0) == (v < (1 << n)) and got == orc.r1cs_verify(og, orc.transcript(b"RangeProofTest"), RANGE, V, proof, param=n)
     gens.close()
+
+
+@pytest.mark.gpu
+def test_gpu_shuffle_config5_full_size(gpu_ctx, orc):
+    """BASELINE config 5: k-shuffle with 2^16 multipliers (k = 32769), prove + verify on one B200.  The oracle prover
+    would take tens of seconds at this size, so parity is checked through the independent verifier: the proof made
+    on the GPU path must be accepted by the oracle's verifier (a 196 655-term CPU MSM) and by the GPU verifier, and a
+    damaged proof / a non-permutation must be rejected by both."""
+    import bulletproofs_b200 as bp
+    k = 32769                                                                           # 2(k-1) = 65 536 multipliers (benches/r1cs.rs:52-67)
+    gens = bp.Gens(gpu_ctx, 65536, 1); og = orc.gens(65536, 1)
+    rnd = random.Random(5)
+    inp = [rnd.randrange(1 << 64) for _ in range(k)]; out = inp[:]; rnd.shuffle(out)
+    bl = b"".join(le(rnd.randrange(l)) for _ in range(2 * k))
+
+    def tr():
+        t = bp.Transcript(b"ShuffleBenchmark"); t.append_message(b"dom-sep", b"ShuffleProof"); t.append_u64(b"k", k); return t
+
+    def otr():
+        t = orc.transcript(b"ShuffleBenchmark"); t = orc.transcript_append(t, b"dom-sep", b"ShuffleProof"); return orc.transcript_append(t, b"k", le(k, 8))
+
+    rc, proof, V = bp.r1cs_prove(gpu_ctx, gens, tr(), bp.GADGET_SHUFFLE, inp + out, bl)
+    assert rc == 0 and len(proof) == 1 + 32 * 14 + 32 * 34                              # 1537 bytes (SURVEY.md §8 table)
+    assert bp.r1cs_verify(gpu_ctx, gens, tr(), bp.GADGET_SHUFFLE, V, proof) == 0
+    assert orc.r1cs_verify(og, otr(), SHUFFLE, V, proof) == 0
+    b = bytearray(proof); b[700] ^= 1
+    assert bp.r1cs_verify(gpu_ctx, gens, tr(), bp.GADGET_SHUFFLE, V, bytes(b)) != 0
+    Vb = bytearray(V); Vb[5 * 32 + 1] ^= 1                                              # a different committed input: no longer a permutation
+    assert bp.r1cs_verify(gpu_ctx, gens, tr(), bp.GADGET_SHUFFLE, bytes(Vb), proof) != 0
+    gens.close()

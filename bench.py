@@ -296,6 +296,17 @@ def main():
     T_terms = 2 + 2 * N_BITS * M_PARTIES + BATCH * (4 + 2 * k_lg + M_PARTIES)
     alg_bytes_step = BATCH * (32 * (9 + 2 * k_lg) + 32 * M_PARTIES + 1) + 32 * (2 * N_BITS * M_PARTIES + 2)     # SURVEY.md §8(d), per verified batch
     alg_bytes = 64 * T_terms + 32 if dom.startswith("k_msm") else alg_bytes_step                                     # SURVEY.md §8(d), MSM of T terms
+    # the roofline that actually binds: IMAD.WIDE.U32 issue (1 per 4 cycles per SM sub-partition, measured 9.25e12 thread-level
+    # wide multiply-adds/s on this pool's B200, profiles/r1_imad_peak.md).  Wide multiplies per verified batch, counted from the
+    # kernels' formulas: fe_mul 72, fe_sq 44, Montgomery product 192.
+    W_win = (255 + 10) // 11; pts = BATCH * (4 + 2 * k_lg + M_PARTIES); Nv = N_BITS * M_PARTIES
+    wide = (pts * (257 * 44 + 29 * 72)                      # decompress: one 2^252-3 exponentiation + decode + Niels form per point
+            + T_terms * W_win * 7 * 72                       # bucket accumulation: one mixed addition per term and window
+            + W_win * (59 * 64 + 1) * 9 * 72                 # bucket reduction: 59 additions per thread, 64 threads per window
+            + BATCH * (Nv * 7 + (4 + 2 * k_lg + M_PARTIES) * 3 + 110) * 192)   # scalar assembly + transcript head (Montgomery products)
+    INT_PEAK = 9.25e12
+    int_pipe = {"unit": "wide multiply-adds/s (IMAD.WIDE.U32, thread level)", "per_step": wide, "achieved": wide * (value / world / BATCH), "peak": INT_PEAK,
+                "frac": wide * (value / world / BATCH) / INT_PEAK, "peak_source": "measured, benchmarks/imad_microbench.cu (profiles/r1_imad_peak.md)"}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -308,6 +319,7 @@ def main():
                 "algorithmic_bytes_per_launch": alg_bytes, "units_per_launch": f"{T_terms} MSM terms x 64 B + 32 B" if dom.startswith("k_msm") else f"{BATCH} proofs",
                 "kernel_ms": dom_ms, "kernel_share_of_step": prof[dom][0] / total_ms,
                 "whole_step": {"algorithmic_bytes": alg_bytes_step, "achieved_GBps_at_value": alg_bytes_step * (value / world / BATCH) / 1e9},
+                "int_pipe": int_pipe,
                 "note": "integer-pipe bound path (IMAD.WIDE field multiplies): the HBM fraction is reported as BASELINE.json asks; issue-slot / FMA-pipe utilisation per kernel is in profiles/",
                 "per_kernel_ms_per_step": {k: round(v[0] / psteps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}}
 

@@ -123,7 +123,10 @@ int msm_core(bp_ctx *ctx, const MsmArgs &a, ge_ext *d_results) {
                                                                 n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>()));
     unsigned rthreads = nb >= 64 ? 64 : 32;      // two warps per segment: fewer scan/tree additions per useful bucket addition
     LAUNCH(ctx, KID_MSM_REDUCE, k_msm_reduce<<<(unsigned)segs, rthreads, 0, s>>>(ctx->buckets.as<ge_ext>(), nb, ctx->wsums.as<ge_ext>()));
-    LAUNCH(ctx, KID_MSM_COMBINE, k_msm_combine<<<blocks_for(a.n_msm, 32), 32, 0, s>>>(ctx->wsums.as<ge_ext>(), a.n_msm, c, W, d_results));
+    if (a.n_msm <= 256)      // few MSMs: the Horner chain is pure latency -> four cooperating lanes per MSM
+        LAUNCH(ctx, KID_MSM_COMBINE, k_msm_combine4<<<blocks_for(a.n_msm, 8), 32, 0, s>>>(ctx->wsums.as<ge_ext>(), a.n_msm, c, W, d_results));
+    else
+        LAUNCH(ctx, KID_MSM_COMBINE, k_msm_combine<<<blocks_for(a.n_msm, 32), 32, 0, s>>>(ctx->wsums.as<ge_ext>(), a.n_msm, c, W, d_results));
     return BP_OK;
 }
 

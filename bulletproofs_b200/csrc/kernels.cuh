@@ -272,6 +272,53 @@ __global__ void k_msm_combine(const ge_ext *__restrict__ window_sums, uint32_t n
     st_ext(results + m, acc);
 }
 
+// pass 6, latency-optimised form for few MSMs: four lanes per MSM, lane q holds coordinate q of the running point
+// (X, Y, Z, T).  A doubling is then one squaring and one multiplication deep (the four squarings and the four products
+// of the HWCD formulas run on the four lanes) plus two shuffle rounds, instead of eight field operations in sequence;
+// the 253-doubling Horner chain is the longest dependency chain of a verified batch.
+__device__ __forceinline__ fe shfl_fe4(const fe &v, int src) {
+    fe r;
+#pragma unroll
+    for (int i = 0; i < 8; i++) r.v[i] = __shfl_sync(0xffffffffu, v.v[i], src, 4);
+    return r;
+}
+__device__ __forceinline__ fe sel_fe(bool pick_b, const fe &a, const fe &b) { return fe_select(a, b, pick_b); }
+__global__ void __launch_bounds__(32) k_msm_combine4(const ge_ext *__restrict__ window_sums, uint32_t n_msm, int c, int W, ge_ext *__restrict__ results) {
+    uint32_t lane = threadIdx.x & 31, q = lane & 3;
+    uint32_t m = blockIdx.x * 8 + (lane >> 2);
+    bool active = m < n_msm;
+    const ge_ext *R = window_sums + (size_t)(active ? m : n_msm - 1) * W;       // idle groups shadow the last MSM (shuffles need every lane)
+    const fe d2 = fe_const_d2();
+    fe cur = ld_fe(&R[W - 1].X + q);
+#pragma unroll 1
+    for (int w = W - 2; w >= 0; w--) {
+#pragma unroll 1
+        for (int i = 0; i < c; i++) {
+            // doubling: A = X^2, B = Y^2, ZZ = Z^2, D = (X+Y)^2 on lanes 0..3
+            fe x = shfl_fe4(cur, 0), y = shfl_fe4(cur, 1);
+            fe sq = fe_sq(sel_fe(q == 3, cur, fe_add(x, y)));
+            fe A = shfl_fe4(sq, 0), B = shfl_fe4(sq, 1), ZZ = shfl_fe4(sq, 2), D = shfl_fe4(sq, 3);
+            fe H = fe_add(A, B), E = fe_sub(D, H), G = fe_sub(B, A), F = fe_sub(G, fe_dbl(ZZ)), Hn = fe_neg(H);
+            // X3 = E F, Y3 = G Hn, Z3 = F G, T3 = E Hn
+            fe o1 = sel_fe(q == 1, sel_fe(q == 2, E, F), G), o2 = sel_fe(q == 0, sel_fe(q == 2, Hn, G), F);
+            cur = fe_mul(o1, o2);
+        }
+        // addition of the window sum (extended, from memory): lanes compute (Y1-X1)(Y2-X2), (Y1+X1)(Y2+X2), Z1 Z2, T1 (2d T2)
+        const ge_ext *P2 = R + w;
+        fe X2 = ld_fe(&P2->X), Y2 = ld_fe(&P2->Y), Z2 = ld_fe(&P2->Z), T2d = fe_mul(ld_fe(&P2->T), d2);
+        fe x1 = shfl_fe4(cur, 0), y1 = shfl_fe4(cur, 1);
+        fe a = sel_fe(q >= 2, sel_fe(q == 1, fe_sub(y1, x1), fe_add(y1, x1)), cur);
+        fe b = sel_fe(q == 1, sel_fe(q == 2, sel_fe(q == 3, fe_sub(Y2, X2), T2d), Z2), fe_add(Y2, X2));
+        fe pr = fe_mul(a, b);
+        fe A = shfl_fe4(pr, 0), B = shfl_fe4(pr, 1), Dh = shfl_fe4(pr, 2), C = shfl_fe4(pr, 3);
+        fe D = fe_dbl(Dh), E = fe_sub(B, A), F = fe_sub(D, C), G = fe_add(D, C), H = fe_add(B, A);
+        // X3 = E F, Y3 = G H, Z3 = F G, T3 = E H
+        fe o1 = sel_fe(q == 1, sel_fe(q == 2, E, F), G), o2 = sel_fe(q == 0, sel_fe(q == 2, H, G), F);
+        cur = fe_mul(o1, o2);
+    }
+    if (active) st_fe(&results[m].X + q, cur);
+}
+
 // ------------------------------------------------------------------ K4: IPP generator fold
 // out[i] = s_lo[i] * P[i] + s_hi[i] * P[half + i], written back to P[i] in affine Niels form
 // (InnerProductProof::create's G/H fold, /root/reference/src/inner_product_proof.rs:127-134,177-178).

@@ -56,12 +56,46 @@ __device__ __forceinline__ ge_ext shfl_down_ext(const ge_ext &p, int d) {
     return r;
 }
 
+// ------------------------------------------------------------------ TMA staging of the streaming byte arrays
+// The scalar and compressed-point arrays are read once, front to back.  Each block stages its contiguous tile
+// (32 B per thread) into shared memory with ONE bulk asynchronous copy (cp.async.bulk: the TMA engine, SASS UBLKCP)
+// signalled through an mbarrier, instead of one 2x128-bit global load pair per thread; threads then read their
+// record from shared memory.  src must be 16-byte aligned, bytes a multiple of 16 (records are 32 B).
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_stage_tile(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+    uint32_t b = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+    }
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(b) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void lds32(uint8_t dst[32], const uint8_t *smem_src) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(smem_src);
+    uint4 a = p[0], b = p[1];
+    uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    memcpy(dst, w, 32);
+}
+
 // ------------------------------------------------------------------ K1: batched Ristretto decompress
 // in: n x 32 B compressed.  out: n affine-Niels points (identity when invalid), ok[i] in {0,1}.
 __global__ void __launch_bounds__(128) k_decompress(const uint8_t *__restrict__ in, size_t n, ge_niels *__restrict__ out, uint8_t *__restrict__ ok) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(128) uint8_t tile[128 * 32];
+    __shared__ __align__(8) uint64_t bar;
+    size_t base = (size_t)blockIdx.x * blockDim.x, i = base + threadIdx.x;
+    uint32_t cnt = (uint32_t)min((size_t)blockDim.x, n - base);
+    tma_stage_tile(tile, in + 32 * base, 32u * cnt, &bar);
     if (i >= n) return;
-    uint8_t s[32]; ld32(s, in + 32 * i);
+    uint8_t s[32]; lds32(s, tile + 32 * threadIdx.x);
     fe x, y; bool valid = ge_decode(x, y, s);
     ge_niels q = valid ? ge_to_niels_affine(x, y) : ge_niels_identity();
     st_niels(out + i, q);
@@ -116,9 +150,12 @@ __device__ __forceinline__ uint32_t msm_of_term(const uint32_t *__restrict__ off
 // pass 1: histogram.  One thread per term; scalars are 32-byte canonical little-endian.
 __global__ void __launch_bounds__(256) k_msm_count(const uint8_t *__restrict__ scalars, const uint32_t *__restrict__ offsets, uint32_t n_msm, uint32_t T,
                                                    int c, int W, uint32_t *__restrict__ counts, uint32_t *__restrict__ msm_err) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(128) uint8_t tile[256 * 32];
+    __shared__ __align__(8) uint64_t bar;
+    uint32_t base = blockIdx.x * blockDim.x, t = base + threadIdx.x;
+    tma_stage_tile(tile, scalars + 32 * (size_t)base, 32u * min(blockDim.x, T - base), &bar);
     if (t >= T) return;
-    uint8_t sb[32]; ld32(sb, scalars + 32 * (size_t)t);
+    uint8_t sb[32]; lds32(sb, tile + 32 * threadIdx.x);
     sc s = sc_load(sb);
     uint32_t msm = n_msm == 1 ? 0u : msm_of_term(offsets, n_msm, t);
     if (sc_geq_l(s)) { if (msm_err) atomicOr(msm_err + msm, 2u); return; }       // non-canonical scalar
@@ -180,9 +217,12 @@ __global__ void __launch_bounds__(256) k_msm_order(const uint32_t *__restrict__ 
 // pass 3: scatter term ids (sign in bit 31) into their bucket's slice
 __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *__restrict__ scalars, const uint32_t *__restrict__ offsets, uint32_t n_msm, uint32_t T,
                                                      int c, int W, uint32_t *__restrict__ cursor, uint32_t *__restrict__ sorted) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(128) uint8_t tile[256 * 32];
+    __shared__ __align__(8) uint64_t bar;
+    uint32_t base = blockIdx.x * blockDim.x, t = base + threadIdx.x;
+    tma_stage_tile(tile, scalars + 32 * (size_t)base, 32u * min(blockDim.x, T - base), &bar);
     if (t >= T) return;
-    uint8_t sb[32]; ld32(sb, scalars + 32 * (size_t)t);
+    uint8_t sb[32]; lds32(sb, tile + 32 * threadIdx.x);
     sc s = sc_load(sb);
     if (sc_geq_l(s)) return;
     uint32_t msm = n_msm == 1 ? 0u : msm_of_term(offsets, n_msm, t);

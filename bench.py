@@ -72,36 +72,44 @@ def make_workload(count, rank):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe): one `nvidia-smi -lms 50`
+    process, every line stamped on arrival; stop() summarises the samples that fell inside mark_begin()..mark_end() windows."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+        self.index, self.samples, self.windows, self.proc = index, [], [], None
 
     def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.1)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index), "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                f = [x.strip() for x in line.split(",")]
+                if len(f) >= 8:
+                    self.samples.append((time.perf_counter(), f))
+        except Exception:
+            pass
+
+    def mark_begin(self):
+        self.windows.append([time.perf_counter(), None])
+
+    def mark_end(self):
+        self.windows[-1][1] = time.perf_counter()
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
-        sm = sorted(int(float(s[1])) for s in self.samples if len(s) >= 8)
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=3)
+        inside = [f for t, f in self.samples if any(a <= t <= (b or 1e30) for a, b in self.windows)] or [f for _, f in self.samples]
+        sm = sorted(int(float(f[1])) for f in inside)
         reasons = set()
-        for s in self.samples:
-            if len(s) >= 8:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(self.samples[0][2])) if self.samples else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        for f in inside:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(float(inside[0][2])) if inside else None,
+                "reasons": sorted(reasons), "samples": len(sm), "power_w_max": max((float(f[3]) for f in inside), default=None)}
 
 
 def run_reference(args, rank, world):
@@ -257,8 +265,10 @@ def main():
         ver[k].run_device(d_proofs[j].data_ptr(), d_vs[j].data_ptr(), d_verdicts[k].data_ptr(), h_ok[k:].data_ptr())
 
     clk = ClockSampler(local); clk.start()
+    time.sleep(0.3)                                   # let the sampler come up before the first timed region
+    clk.mark_begin()
     ms_dev, _, launches, host_issue_dev = timed(step_dev, lambda: None, args.steps, args.warmup)
-    clocks = clk.stop()
+    clk.mark_end()
     assert int(h_ok.min()) == 1 and int(d_verdicts.abs().max()) == 0, "a timed batch did not verify"
     value = world * BATCH * args.steps / (ms_dev * 1e-3)
 
@@ -274,7 +284,10 @@ def main():
             if v.busy:
                 assert not any(v.finish())
 
+    clk.mark_begin()
     ms_e2e, wall_e2e, _, _ = timed(step_e2e, drain_e2e, args.steps, args.warmup)
+    clk.mark_end()
+    clocks = clk.stop()
     e2e_value = world * BATCH * args.steps / (max(ms_e2e * 1e-3, wall_e2e))
     h2d = BATCH * (plen + 32 * M_PARTIES) + bp.TRANSCRIPT_BYTES + 32 + 8 + 4
     d2h = 4 * BATCH + 4
@@ -303,7 +316,7 @@ def main():
     wide = (pts * (257 * 44 + 29 * 72)                      # decompress: one 2^252-3 exponentiation + decode + Niels form per point
             + T_terms * W_win * 7 * 72                       # bucket accumulation: one mixed addition per term and window
             + W_win * (59 * 64 + 1) * 9 * 72                 # bucket reduction: 59 additions per thread, 64 threads per window
-            + BATCH * (Nv * 7 + (4 + 2 * k_lg + M_PARTIES) * 3 + 110) * 192)   # scalar assembly + transcript head (Montgomery products)
+            + BATCH * (Nv * 3 + (4 + 2 * k_lg + M_PARTIES) * 3 + 170) * 192)   # scalar assembly (3 products per generator index) + per-proof head
     INT_PEAK = 9.25e12
     int_pipe = {"unit": "wide multiply-adds/s (IMAD.WIDE.U32, thread level)", "per_step": wide, "achieved": wide * (value / world / BATCH), "peak": INT_PEAK,
                 "frac": wide * (value / world / BATCH) / INT_PEAK, "peak_source": "measured, benchmarks/imad_microbench.cu (profiles/r1_imad_peak.md)"}

@@ -391,8 +391,8 @@ static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t 
         CK(c, cudaMemcpyAsync(c->pow2_tab.p, tab.data(), 64 * sizeof(sc), cudaMemcpyHostToDevice, s)); CK(c, cudaStreamSynchronize(s));
     }
     LAUNCH(c, KID_RP_TRANSCRIPT, k_rp_transcript<<<blocks_for(count, RP_TR_THREADS), RP_TR_THREADS, 0, s>>>(d_proofs, d_commit, g, d_tstate, d_seed, count,
-                                                                                                           c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(), c->rp_status.as<uint32_t>()));
-    LAUNCH(c, KID_RP_SCALARS, k_rp_scalars<<<blocks_for((size_t)count * (g.N + g.D), 128), 128, 0, s>>>(g, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(), c->pow2_tab.as<sc>(), count, c->rp_contrib.as<sc>(), d_scal + (size_t)g.S * 32));
+                                                                                                           c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(), c->pow2_tab.as<sc>(), c->rp_status.as<uint32_t>()));
+    LAUNCH(c, KID_RP_SCALARS, k_rp_scalars<<<blocks_for((size_t)count * (g.N + g.D), 128), 128, 0, s>>>(g, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(), count, c->rp_contrib.as<sc>(), d_scal + (size_t)g.S * 32));
     LAUNCH(c, KID_RP_DECOMPRESS, k_rp_decompress<<<blocks_for((size_t)count * g.D, 128), 128, 0, s>>>(d_proofs, d_commit, g, count, c->niels.as<ge_niels>(), c->rp_status.as<uint32_t>()));
     LAUNCH(c, KID_RP_STATIC_REDUCE, k_rp_static_reduce<<<g.S, 128, 0, s>>>(c->rp_contrib.as<sc>(), g.S, count, d_scal));
     if (c->pidx_key[0] != g.n || c->pidx_key[1] != g.m || c->pidx_key[2] != count || c->pidx_key[3] != gens->cap || c->pidx_key[4] != gens->parties) {

@@ -400,7 +400,7 @@ struct rp_geom { uint32_t n, m, k, N, D, S; uint32_t proof_len; };   // D = 4+2k
 #define RP_TR_THREADS 32
 __global__ void __launch_bounds__(RP_TR_THREADS) k_rp_transcript(const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ commitments, rp_geom g,
                                                                    const uint8_t *__restrict__ tstate, const uint8_t *__restrict__ seed, uint32_t count,
-                                                                   rp_head *__restrict__ heads, sc *__restrict__ tabs, uint32_t *__restrict__ status) {
+                                                                   rp_head *__restrict__ heads, sc *__restrict__ tabs, const sc *__restrict__ pow2, uint32_t *__restrict__ status) {
     __shared__ __align__(16) uint8_t rows[RP_TR_THREADS][204];
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= count) return;
@@ -417,13 +417,13 @@ __global__ void __launch_bounds__(RP_TR_THREADS) k_rp_transcript(const uint8_t *
     rp_transcript(ch, proof, g.k, V, g.n, g.m, tstate, weights, rows[threadIdx.x]);
     status[p] = ch.status;
     heads[p].status = ch.status;
-    if (ch.status == BP_PROOF_OK) rp_scalars_head(heads[p], tabs + (size_t)p * rp_tab_size(g.k, g.m), ch, proof, g.k, g.n, g.m);
+    if (ch.status == BP_PROOF_OK) rp_scalars_head(heads[p], tabs + (size_t)p * rp_tab_size(g.k, g.m), pow2, ch, proof, g.k, g.n, g.m);
 }
 // K5: verification scalars, fully data-parallel: one thread per (proof, term) with term in
 // [0, N) -> (g_i, h_i) and [N, N + D) -> the per-proof scalars.
 //   contrib : count x S Montgomery scalars (weighted static-term scalars: B~, B, G.., H..)
 //   dyn     : count x D canonical scalars, written straight into the MSM scalar array
-__global__ void __launch_bounds__(128) k_rp_scalars(rp_geom g, const rp_head *__restrict__ heads, const sc *__restrict__ tabs, const sc *__restrict__ pow2, uint32_t count,
+__global__ void __launch_bounds__(128) k_rp_scalars(rp_geom g, const rp_head *__restrict__ heads, const sc *__restrict__ tabs, uint32_t count,
                                                     sc *__restrict__ contrib, uint8_t *__restrict__ dyn_scalars) {
     uint32_t per = g.N + g.D;
     size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(128) k_rp_scalars(rp_geom g, const rp_head *__
     bool ok = h.status == BP_PROOF_OK;        // a malformed proof contributes nothing to the combination
     if (i < g.N) {
         sc gg = sc_zero(), hh = sc_zero();
-        if (ok) rp_scalars_gh(h, tabs + (size_t)p * rp_tab_size(g.k, g.m), pow2, i, g.k, g.n, gg, hh);
+        if (ok) rp_scalars_gh(h, tabs + (size_t)p * rp_tab_size(g.k, g.m), i, g.k, gg, hh);
         my[2 + i] = gg; my[2 + g.N + i] = hh;
         if (i == 0) { my[0] = ok ? h.blinding_scalar : sc_zero(); my[1] = ok ? h.basepoint_scalar : sc_zero(); }
     } else {

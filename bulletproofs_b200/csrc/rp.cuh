@@ -84,15 +84,31 @@ struct rp_head {                // Montgomery form; "L" = Lambda = rho * lambda
     sc basepoint_scalar, blinding_scalar;
 };
 
-// Per-proof product tables (global memory, rp_tab_size() scalars per proof) that turn the k-step
-// products of the tail into one lookup pair each.  The k index bits are split in a low group of
-// kl = ceil(k/2) bits and a high group of kh = k - kl bits:
-//   s_lo[v] = prod_{b < kl, bit b of v}  u_sq[k-1-b]        s_hi[v] = prod_{b < kh, bit b of v} u_sq[k-1-kl-b]
-//   y_lo[v] = y^v                                            y_hi[v] = y^(v * 2^kl)
-//   hAz[j]  = rho U^2 z^2 z^j   (j < m)
-// so that  prod_{bits set in i} u^2 = s_hi[i >> kl] * s_lo[i & (2^kl - 1)]  and  y^e likewise.
+// Per-proof product tables (global memory, rp_tab_size() scalars per proof) that turn the tail into three products
+// per generator index.  The k index bits are split in a low group of kl = ceil(k/2) bits (TL = 2^kl values) and a
+// high group of kh = k - kl bits (TH = 2^kh values), i = hi*TL + lo, and ~v is the complement within the group:
+//   s_lo[v] = prod_{b < kl, bit b of v} u_sq[k-1-b]           s_hi[v] = prod_{b < kh, bit b of v} u_sq[k-1-kl-b]
+//   y_lo[v] = y^v                                               y_hi[v] = y^(v*TL)
+//   A_hi[v] = gA * s_hi[v]
+//   P_lo[v] = y_lo[~v] * F_lo(v)                                P_hi[v] = hA * y_hi[~v] * F_hi(v)
+//   Q_lo[v] = y_lo[~v] * s_lo[~v]                               Q_hi[v] = hB * y_hi[~v] * s_hi[~v]
+// with F(i) = 2^(i mod n) z^(i div n) = F_hi(hi) F_lo(lo) (n and TL are powers of two), so that
+//   lambda-weighted  g_i = -zL - A_hi[hi] s_lo[lo],     h_i = zL + P_hi[hi] P_lo[lo] - Q_hi[hi] Q_lo[lo].
 BP_HD uint32_t rp_kl(uint32_t k) { return (k + 1) / 2; }
-BP_HD uint32_t rp_tab_size(uint32_t k, uint32_t m) { uint32_t kl = rp_kl(k); return 2 * ((1u << kl) + (1u << (k - kl))) + m; }
+BP_HD uint32_t rp_tab_size(uint32_t k, uint32_t m) { (void)m; uint32_t kl = rp_kl(k); return 4 * (1u << kl) + 5 * (1u << (k - kl)); }
+struct rp_tabs { sc *s_lo, *A_hi, *P_lo, *P_hi, *Q_lo, *Q_hi, *s_hi, *y_lo, *y_hi; };
+BP_HD rp_tabs rp_tab_ptrs(sc *tab, uint32_t k) {
+    uint32_t kl = rp_kl(k), TL = 1u << kl, TH = 1u << (k - kl);
+    rp_tabs t; t.s_lo = tab; t.A_hi = t.s_lo + TL; t.P_lo = t.A_hi + TH; t.P_hi = t.P_lo + TL; t.Q_lo = t.P_hi + TH; t.Q_hi = t.Q_lo + TL;
+    t.s_hi = t.Q_hi + TH; t.y_lo = t.s_hi + TH; t.y_hi = t.y_lo + TL;
+    return t;
+}
+
+BP_HD sc rp_pow_small(const sc &base0, uint32_t e) {                // base^e by square-and-multiply
+    sc r = sc_mont_one(), base = base0;
+    for (; e; e >>= 1) { if (e & 1u) r = sc_mm(r, base); if (e > 1) base = sc_mm(base, base); }
+    return r;
+}
 
 // sum_{i<n} x^i for n a power of two (util.rs:240-256), Montgomery form
 BP_HD sc rp_sum_of_powers_pow2(const sc &x, uint64_t n) {
@@ -114,13 +130,13 @@ BP_HD sc rp_sum_of_powers_pow2(const sc &x, uint64_t n) {
     } while (0)
 
 // Sequential head: shared products and tables of one proof
-BP_HDN void rp_scalars_head(rp_head &h, sc *tab, const rp_challenges &ch, const uint8_t *proof, uint32_t k, uint32_t n, uint32_t m) {
+BP_HDN void rp_scalars_head(rp_head &h, sc *tab, const sc *pow2, const rp_challenges &ch, const uint8_t *proof, uint32_t k, uint32_t n, uint32_t m) {
     const uint8_t *ab = proof + 224 + 64 * k;
     sc a = sc_to_mont(sc_load(ab)), b = sc_to_mont(sc_load(ab + 32));
     sc t_x = sc_to_mont(sc_load(proof + 128)), t_x_bl = sc_to_mont(sc_load(proof + 160)), e_bl = sc_to_mont(sc_load(proof + 192));
     h.z = ch.z; h.zz = sc_mm(ch.z, ch.z);
     uint32_t kl = rp_kl(k), kh = k - kl, TL = 1u << kl, TH = 1u << kh;
-    sc *s_lo = tab, *s_hi = tab + TL, *y_lo = s_hi + TH, *y_hi = y_lo + TL, *hAz = y_hi + TH;
+    rp_tabs T = rp_tab_ptrs(tab, k);
     sc U = sc_mont_one(), Y = sc_mont_one(), ypow2[BP_MAX_LG_N];
     h.pre[0] = sc_mont_one();
     for (uint32_t j = 0; j < k; j++) {
@@ -132,18 +148,31 @@ BP_HDN void rp_scalars_head(rp_head &h, sc *tab, const rp_challenges &ch, const 
     h.suf[k] = sc_mont_one();
     for (int j = (int)k - 1; j >= 0; j--) h.suf[j] = sc_mm(h.suf[j + 1], h.u_sq[j]);   // prod_{j' >= j} u^2
     // bit b of the index i <-> challenge k-1-b (inner_product_proof.rs:241-250)
-    RP_BUILD_TABLE(s_lo, kl, h.u_sq[(k - 1) - b_]);
-    RP_BUILD_TABLE(s_hi, kh, h.u_sq[(k - 1) - kl - b_]);
-    RP_BUILD_TABLE(y_lo, kl, ypow2[b_]);
-    RP_BUILD_TABLE(y_hi, kh, ypow2[kl + b_]);
+    RP_BUILD_TABLE(T.s_lo, kl, h.u_sq[(k - 1) - b_]);
+    RP_BUILD_TABLE(T.s_hi, kh, h.u_sq[(k - 1) - kl - b_]);
+    RP_BUILD_TABLE(T.y_lo, kl, ypow2[b_]);
+    RP_BUILD_TABLE(T.y_hi, kh, ypow2[kl + b_]);
     sc lambda = sc_mm(h.pre[k], Y);
     h.L = sc_mm(ch.rho, lambda); h.zL = sc_mm(ch.z, h.L);
     h.Lx = sc_mm(h.L, ch.x); h.Lcx = sc_mm(h.Lx, ch.c); h.Lcxx = sc_mm(h.Lcx, ch.x); h.Lczz = sc_mm(sc_mm(h.L, ch.c), h.zz);
     sc rhoU = sc_mm(ch.rho, U);
     h.gA = sc_mm(sc_mm(a, rhoU), Y);                                // a rho U y^(N-1)
     h.hB = sc_mm(b, rhoU);                                          // b rho U
-    hAz[0] = sc_mm(sc_mm(rhoU, U), h.zz);                           // rho U^2 z^2 z^j
-    for (uint32_t j = 1; j < m; j++) hAz[j] = sc_mm(hAz[j - 1], ch.z);
+    sc hA = sc_mm(sc_mm(rhoU, U), h.zz);                            // rho U^2 z^2
+    // F(i) = 2^(i mod n) z^(i div n) split over the two index groups
+    for (uint32_t v = 0; v < TL; v++) {
+        sc F = sc_mm(pow2[v % n], rp_pow_small(ch.z, v / n));       // v < TL: (v mod n, v div n)
+        T.P_lo[v] = sc_mm(T.y_lo[v ^ (TL - 1)], F);
+        T.Q_lo[v] = sc_mm(T.y_lo[v ^ (TL - 1)], T.s_lo[v ^ (TL - 1)]);
+    }
+    for (uint32_t v = 0; v < TH; v++) {
+        uint64_t idx = (uint64_t)v << kl;                           // i = v*TL: (i mod n, i div n)
+        sc F = sc_mm(pow2[idx % n], rp_pow_small(ch.z, (uint32_t)(idx / n)));
+        sc yc = T.y_hi[v ^ (TH - 1)];
+        T.A_hi[v] = sc_mm(h.gA, T.s_hi[v]);
+        T.P_hi[v] = sc_mm(sc_mm(hA, yc), F);
+        T.Q_hi[v] = sc_mm(sc_mm(h.hB, yc), T.s_hi[v ^ (TH - 1)]);
+    }
     h.rhoY = sc_mm(ch.rho, Y);
     // delta(y,z) = (z - z^2) sum y^i - z^3 (2^n - 1) sum z^j          (mod.rs:587-593)
     sc sum_y = rp_sum_of_powers_pow2(ch.y, (uint64_t)n * m), sum_z = rp_sum_of_powers_pow2(ch.z, m);
@@ -155,24 +184,14 @@ BP_HDN void rp_scalars_head(rp_head &h, sc *tab, const rp_challenges &ch, const 
     h.basepoint_scalar = sc_mm(h.L, bs); h.blinding_scalar = sc_mm(h.L, bl);
 }
 
-BP_HD sc rp_pow_small(const sc &base0, uint32_t e) {                // base^e by square-and-multiply
-    sc r = sc_mont_one(), base = base0;
-    for (; e; e >>= 1) { if (e & 1u) r = sc_mm(r, base); if (e > 1) base = sc_mm(base, base); }
-    return r;
-}
-
 // Data-parallel tail: weighted g_i and h_i for generator pair i in [0, N) (mod.rs:415-417), Montgomery form.
-// pow2 = table of 2^e (e < 64) in Montgomery form.  Seven products per index.
-BP_HD void rp_scalars_gh(const rp_head &h, const sc *tab, const sc *pow2, uint32_t i, uint32_t k, uint32_t n, sc &g, sc &hh) {
-    uint32_t kl = rp_kl(k), kh = k - kl, TL = 1u << kl, TH = 1u << kh;
-    const sc *s_lo = tab, *s_hi = tab + TL, *y_lo = s_hi + TH, *y_hi = y_lo + TL, *hAz = y_hi + TH;
-    uint32_t lo = i & (TL - 1), hi = i >> kl, nlo = lo ^ (TL - 1), nhi = hi ^ (TH - 1);
-    sc s = sc_mm(s_hi[hi], s_lo[lo]);                               // lambda-free s_i: prod over set bits
-    sc s_rev = sc_mm(s_hi[nhi], s_lo[nlo]);                         // prod over clear bits (= index N-1-i)
-    sc yy = sc_mm(y_hi[nhi], y_lo[nlo]);                            // y^(N-1-i)
-    uint32_t j = i / n, ii = i % n;
-    g = sc_sub(sc_neg(h.zL), sc_mm(h.gA, s));
-    hh = sc_add(h.zL, sc_mm(yy, sc_sub(sc_mm(hAz[j], pow2[ii]), sc_mm(h.hB, s_rev))));
+// Three products per index (see the table definitions above).
+BP_HD void rp_scalars_gh(const rp_head &h, const sc *tab, uint32_t i, uint32_t k, sc &g, sc &hh) {
+    uint32_t kl = rp_kl(k), TL = 1u << kl;
+    rp_tabs T = rp_tab_ptrs(const_cast<sc *>(tab), k);
+    uint32_t lo = i & (TL - 1), hi = i >> kl;
+    g = sc_sub(sc_neg(h.zL), sc_mm(T.A_hi[hi], T.s_lo[lo]));
+    hh = sc_sub(sc_add(h.zL, sc_mm(T.P_hi[hi], T.P_lo[lo])), sc_mm(T.Q_hi[hi], T.Q_lo[lo]));
 }
 
 // Per-proof ("dynamic") scalars in MSM order A, S, T_1, T_2, L_0..L_{k-1}, R_0..R_{k-1}, V_0..V_{m-1}

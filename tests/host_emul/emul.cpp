@@ -65,10 +65,10 @@ int emul_rp_scalars(const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t
     if (ch.status) return (int)ch.status;
     std::vector<sc> tab(rp_tab_size(k, m)), pow2(64);
     for (int e = 0; e < 64; e++) pow2[e] = sc_mont_from_u64(1ULL << e);
-    rp_scalars_head(h, tab.data(), ch, proof, k, n, m);
+    rp_scalars_head(h, tab.data(), pow2.data(), ch, proof, k, n, m);
     uint32_t N = n * m, S = 2 + 2 * N, D = 4 + 2 * k + m;
     sc_store(out, sc_from_mont(h.blinding_scalar)); sc_store(out + 32, sc_from_mont(h.basepoint_scalar));
-    for (uint32_t i = 0; i < N; i++) { sc g, hh; rp_scalars_gh(h, tab.data(), pow2.data(), i, k, n, g, hh); sc_store(out + 32 * (2 + i), sc_from_mont(g)); sc_store(out + 32 * (2 + N + i), sc_from_mont(hh)); }
+    for (uint32_t i = 0; i < N; i++) { sc g, hh; rp_scalars_gh(h, tab.data(), i, k, g, hh); sc_store(out + 32 * (2 + i), sc_from_mont(g)); sc_store(out + 32 * (2 + N + i), sc_from_mont(hh)); }
     for (uint32_t i = 0; i < D; i++) sc_store(out + 32 * (S + i), sc_from_mont(rp_scalars_dynamic(h, i, k)));
     return 0;
 }

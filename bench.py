@@ -50,9 +50,9 @@ def effective_cores():
 
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture
-# profiles/r1_v2_ncu_full.md; the scratch arrays (sorted ids, buckets, contrib) make it larger than the algorithmic bytes
-NCU_TRAFFIC_BYTES = {"k_msm_accumulate": 3.62e6, "k_msm_reduce": 3.37e6, "k_msm_combine": 0.048e6, "k_rp_transcript": 1.05e6,
-                     "k_rp_scalars": 2.84e6, "k_rp_decompress": 0.825e6, "k_rp_static_reduce": 4.27e6}
+# profiles/r1_final_ncu_full.md; the scratch arrays (sorted ids, buckets, contrib) make it larger than the algorithmic bytes
+NCU_TRAFFIC_BYTES = {"k_msm_accumulate": 3.72e6, "k_msm_reduce": 3.37e6, "k_msm_combine": 0.025e6, "k_rp_transcript": 1.05e6,
+                     "k_rp_scalars": 2.93e6, "k_rp_decompress": 0.83e6, "k_rp_static_reduce": 4.27e6}
 
 
 def make_workload(count, rank):
@@ -300,7 +300,7 @@ def main():
     prof = ctxs[0].prof_report(); ctxs[0].prof_enable(False)
     total_ms = sum(v[0] for v in prof.values())
     # dominant kernel = the Pippenger bucket accumulation: the largest share of executed warp instructions of a step
-    # (33 % in the committed ncu capture, profiles/r1_v2_ncu_full.md).  The single-warp k_msm_combine and the 32-warp
+    # (27 % in the committed ncu capture profiles/r1_final_ncu_full.md, next to the per-proof decompressions' 34 %; it is the MSM kernel north_star names).  The single-warp k_msm_combine and the 32-warp
     # k_rp_transcript have longer durations when a batch runs alone, but they are latency chains that overlap with the
     # other batches in flight and use <1 % of the issue slots.
     dom = "k_msm_accumulate" if "k_msm_accumulate" in prof else max(prof, key=lambda k: prof[k][0])

@@ -101,6 +101,10 @@ def host_lib():
         H.bph_ipp_create.argtypes = [_vp, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _sz, _u8p]
         H.bph_ipp_verify.restype = _int
         H.bph_ipp_verify.argtypes = [_vp, _u8p, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _sz]
+        H.bph_linear_create.restype = _int
+        H.bph_linear_create.argtypes = [_vp, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p, _sz, _u8p]
+        H.bph_linear_verify.restype = _int
+        H.bph_linear_verify.argtypes = [_vp, _u8p, _u8p, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _sz]
         H.bph_r1cs_prove.restype = _int
         H.bph_r1cs_prove.argtypes = [_vp, _vp, _sz, _sz, _u8p, _int, _u8p, _u8p, _sz, _c.c_uint64, _c.c_uint64, _u8p, _u8p, _c.POINTER(_sz), _u8p]
         H.bph_r1cs_verify.restype = _int
@@ -350,6 +354,23 @@ def ipp_create(ctx: Context, transcript: Transcript, Q: bytes, Gf: bytes, Hf: by
 
 def ipp_verify(ctx: Context, transcript: Transcript, n: int, Gf: bytes, Hf: bytes, P: bytes, Q: bytes, G: bytes, H: bytes, proof: bytes) -> int:
     rc = host_lib().bph_ipp_verify(ctx._h, transcript.state, n, Gf, Hf, P, Q, G, H, proof, len(proof))
+    if rc < 0:
+        raise BpError(rc, lib().bp_last_error(ctx._h).decode())
+    return rc
+
+
+def linear_create(ctx: Context, transcript: Transcript, seed: bytes, C: bytes, r: bytes, a: bytes, b: bytes, G: bytes, F: bytes, B: bytes):
+    """LinearProof::create with rng = ChaChaRng::from_seed(seed); returns (status, proof bytes)."""
+    n = len(a) // 32
+    out = ctypes.create_string_buffer(32 * (2 * (n.bit_length() - 1) + 3))
+    rc = host_lib().bph_linear_create(ctx._h, transcript.state, seed, C, r, a, b, G, F, B, n, out)
+    if rc < 0:
+        raise BpError(rc, lib().bp_last_error(ctx._h).decode())
+    return rc, out.raw
+
+
+def linear_verify(ctx: Context, transcript: Transcript, proof: bytes, C: bytes, G: bytes, F: bytes, B: bytes, b: bytes) -> int:
+    rc = host_lib().bph_linear_verify(ctx._h, transcript.state, proof, len(proof), C, G, F, B, b, len(b) // 32)
     if rc < 0:
         raise BpError(rc, lib().bp_last_error(ctx._h).decode())
     return rc

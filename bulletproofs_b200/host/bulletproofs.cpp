@@ -158,6 +158,122 @@ ProofError InnerProductProof::from_bytes(const uint8_t *s, size_t len, InnerProd
     return ProofError::Ok;
 }
 
+// ------------------------------------------------------------------ LinearProof
+// The device session of the inner-product prover is reused: G stays on the device and is folded there; the session's
+// H vector is filled with copies of B and its Q slot holds F, so that one bp_ipp_lr call gives
+//   L = <a_L, G_R> + s_j B + c_L F   and   R = <a_R, G_L> + t_j B + c_R F        (linear_proof.rs:96-107).
+static void linear_transcript_header(Transcript &t, size_t n, const CompressedRistretto &C, const std::vector<Scalar> &b, const std::vector<CompressedRistretto> &G,
+                                     const CompressedRistretto &F, const CompressedRistretto &B) {
+    t.innerproduct_domain_sep(n);
+    t.append_point("C", C);
+    for (const Scalar &bi : b) t.append_scalar("b_i", bi);
+    for (const CompressedRistretto &g : G) t.append_point("G_i", g);
+    t.append_point("F", F); t.append_point("B", B);
+}
+ProofError LinearProof::create(Device &dev, Transcript &t, Rng &rng, const CompressedRistretto &C, Scalar r, std::vector<Scalar> a, std::vector<Scalar> b,
+                               const std::vector<CompressedRistretto> &G, const CompressedRistretto &F, const CompressedRistretto &B, LinearProof &out) {
+    size_t n = b.size(), n0 = n;
+    if (G.size() != n) return ProofError::InvalidGeneratorsLength;
+    if (a.size() != n || n == 0 || (n & (n - 1))) return ProofError::InvalidInputLength;
+    linear_transcript_header(t, n, C, b, G, F, B);
+    out.L_vec.clear(); out.R_vec.clear();
+    bp_ipp *sess = nullptr;
+    if (n0 >= 2) {
+        std::vector<CompressedRistretto> H(n0, B);
+        check(bp_ipp_begin_points(dev.ctx, G[0].data(), H[0].data(), n0, F.data(), &sess), dev.ctx, "bp_ipp_begin_points");
+    }
+    try {
+        Scalar one = Scalar::one(), zero = Scalar::zero();
+        while (n != 1) {
+            n /= 2;
+            std::vector<Scalar> aL(a.begin(), a.begin() + n), aR(a.begin() + n, a.begin() + 2 * n), bL(b.begin(), b.begin() + n), bR(b.begin() + n, b.begin() + 2 * n);
+            Scalar c_L = inner_product(aL, bR), c_R = inner_product(aR, bL);
+            Scalar s_j = Scalar::random(rng), t_j = Scalar::random(rng);
+            std::vector<Scalar> sL(2 * n + 1, zero), sR(2 * n + 1, zero);
+            for (size_t i = 0; i < n; i++) { sL[i] = aL[i]; sR[i] = aR[i]; }
+            sL[n] = s_j; sR[n] = t_j; sL[2 * n] = c_L; sR[2 * n] = c_R;
+            CompressedRistretto L, R;
+            check(bp_ipp_lr(sess, n, pack(sL).data(), pack(sR).data(), L.data(), R.data()), dev.ctx, "bp_ipp_lr");
+            out.L_vec.push_back(L); out.R_vec.push_back(R);
+            t.append_point("L", L); t.append_point("R", R);
+            Scalar x = t.challenge_scalar("x_j"), x_inv = x.invert();
+            for (size_t i = 0; i < n; i++) { a[i] = aL[i] + x_inv * aR[i]; b[i] = bL[i] + x * bR[i]; }      // :124-126
+            check(bp_ipp_fold(sess, n, one.to_bytes().data(), x.to_bytes().data(), one.to_bytes().data(), zero.to_bytes().data(), 0), dev.ctx, "bp_ipp_fold");   // G_L += x G_R (:127-131)
+            a.resize(n); b.resize(n);
+            r = r + x * s_j + x_inv * t_j;
+        }
+        Scalar s_star = Scalar::random(rng), t_star = Scalar::random(rng);
+        // S = t* B + s* b_0 F + s* G_0   (:143)
+        if (n0 >= 2) {
+            std::vector<Scalar> sL(3, zero), sR = {s_star, t_star, s_star * b[0]};
+            CompressedRistretto junk;
+            check(bp_ipp_lr(sess, 1, pack(sL).data(), pack(sR).data(), junk.data(), out.S.data()), dev.ctx, "bp_ipp_lr");
+        } else {
+            std::vector<Scalar> s3 = {t_star, s_star * b[0], s_star}; uint8_t pts[96];
+            memcpy(pts, B.data(), 32); memcpy(pts + 32, F.data(), 32); memcpy(pts + 64, G[0].data(), 32);
+            check(bp_msm(dev.ctx, pack(s3).data(), pts, 3, out.S.data()), dev.ctx, "bp_msm");
+        }
+        t.append_point("S", out.S);
+        Scalar x_star = t.challenge_scalar("x_star");
+        out.a = s_star + x_star * a[0]; out.r = t_star + x_star * r;
+        if (sess) bp_ipp_end(sess);
+        return ProofError::Ok;
+    } catch (...) { if (sess) bp_ipp_end(sess); throw; }
+}
+ProofError LinearProof::verify(Device &dev, Transcript &t, const CompressedRistretto &C, const std::vector<CompressedRistretto> &G, const CompressedRistretto &F,
+                               const CompressedRistretto &B, std::vector<Scalar> b) const {
+    size_t n = b.size(), lg_n = L_vec.size();
+    if (G.size() != n) return ProofError::InvalidGeneratorsLength;
+    linear_transcript_header(t, n, C, b, G, F, B);
+    if (lg_n >= 32 || n != ((size_t)1 << lg_n)) return ProofError::VerificationError;           // verification_scalars :235-241
+    std::vector<Scalar> x(lg_n), x_inv(lg_n);
+    size_t nm = n;
+    for (size_t j = 0; j < lg_n; j++) {
+        if (!t.validate_and_append_point("L", L_vec[j]) || !t.validate_and_append_point("R", R_vec[j])) return ProofError::VerificationError;
+        x[j] = t.challenge_scalar("x_j");
+        nm /= 2;
+        for (size_t i = 0; i < nm; i++) b[i] = b[i] + x[j] * b[nm + i];
+    }
+    for (size_t j = 0; j < lg_n; j++) x_inv[j] = x[j].invert();
+    t.append_point("S", S);
+    Scalar x_star = t.challenge_scalar("x_star");
+    // expect_S = r B + a b_0 F - x*(C + sum x_j L_j + sum x_j^-1 R_j) + a sum s_i G_i   (:208-218) as one MSM
+    std::vector<Scalar> sc_; std::vector<uint8_t> pts;
+    auto term = [&](const Scalar &s_, const CompressedRistretto &p) { sc_.push_back(s_); pts.insert(pts.end(), p.begin(), p.end()); };
+    term(r, B); term(a * b[0], F); term(-x_star, C);
+    for (size_t j = 0; j < lg_n; j++) term(-(x_star * x[j]), L_vec[j]);
+    for (size_t j = 0; j < lg_n; j++) term(-(x_star * x_inv[j]), R_vec[j]);
+    std::vector<Scalar> s(n); s[0] = Scalar::one();
+    for (size_t i = 1; i < n; i++) { size_t lg_i = 63 - (size_t)__builtin_clzll((unsigned long long)i); s[i] = s[i - ((size_t)1 << lg_i)] * x[(lg_n - 1) - lg_i]; }   // subset_product :272-284
+    for (size_t i = 0; i < n; i++) term(a * s[i], G[i]);
+    CompressedRistretto expect;
+    int rc = bp_msm(dev.ctx, pack(sc_).data(), pts.data(), sc_.size(), expect.data());
+    if (rc == BP_ERR_INVALID_POINT) return ProofError::VerificationError;
+    check(rc, dev.ctx, "bp_msm");
+    uint8_t ok = 0; check(bp_decompress_check_batch(dev.ctx, S.data(), 1, &ok), dev.ctx, "decompress S");       // S.decompress() must succeed (:204)
+    return (ok && expect == S) ? ProofError::Ok : ProofError::VerificationError;
+}
+std::vector<uint8_t> LinearProof::to_bytes() const {
+    std::vector<uint8_t> buf;
+    for (size_t i = 0; i < L_vec.size(); i++) { buf.insert(buf.end(), L_vec[i].begin(), L_vec[i].end()); buf.insert(buf.end(), R_vec[i].begin(), R_vec[i].end()); }
+    buf.insert(buf.end(), S.begin(), S.end());
+    Bytes32 x = a.to_bytes(); buf.insert(buf.end(), x.begin(), x.end());
+    x = r.to_bytes(); buf.insert(buf.end(), x.begin(), x.end());
+    return buf;
+}
+ProofError LinearProof::from_bytes(const uint8_t *s, size_t len, LinearProof &out) {
+    if (len % 32 != 0) return ProofError::FormatError;
+    size_t ne = len / 32;
+    if (ne < 3 || (ne - 3) % 2 != 0) return ProofError::FormatError;
+    size_t lg_n = (ne - 3) / 2;
+    if (lg_n >= 32) return ProofError::FormatError;
+    out.L_vec.resize(lg_n); out.R_vec.resize(lg_n);
+    for (size_t i = 0; i < lg_n; i++) { memcpy(out.L_vec[i].data(), s + 64 * i, 32); memcpy(out.R_vec[i].data(), s + 64 * i + 32, 32); }
+    memcpy(out.S.data(), s + 64 * lg_n, 32);
+    if (!Scalar::from_canonical_bytes(s + 64 * lg_n + 32, out.a) || !Scalar::from_canonical_bytes(s + 64 * lg_n + 64, out.r)) return ProofError::FormatError;
+    return ProofError::Ok;
+}
+
 // ------------------------------------------------------------------ RangeProof
 static Scalar scalar_exp_vartime(const Scalar &x, uint64_t n) {      // util.rs:222-234
     Scalar result = Scalar::one(), aux = x;
@@ -319,6 +435,36 @@ int bph_rangeproof_verify(bp_ctx *ctx, bp_gens *gens, size_t gens_capacity, size
         if (e != ProofError::Ok) return (int)e;
         std::vector<CompressedRistretto> V(m); for (size_t j = 0; j < m; j++) memcpy(V[j].data(), commitments + 32 * j, 32);
         return (int)p.verify_multiple(dev, g, Transcript(transcript), V, n);
+    } catch (const std::exception &) { return -1; }
+}
+static bool load_scalars(const uint8_t *b, size_t n, std::vector<Scalar> &out);
+static std::vector<CompressedRistretto> load_points(const uint8_t *b, size_t n);
+// LinearProof::create with rng = ChaChaRng::from_seed(seed); proof_out = 32*(2 lg n + 3) bytes
+int bph_linear_create(bp_ctx *ctx, uint8_t *transcript, const uint8_t seed[32], const uint8_t C[32], const uint8_t r[32], const uint8_t *a, const uint8_t *b, const uint8_t *G,
+                      const uint8_t F[32], const uint8_t B[32], size_t n, uint8_t *proof_out) {
+    try {
+        Device dev(ctx); Transcript t(transcript); ChaChaRng rng(seed);
+        std::vector<Scalar> av, bv; Scalar rr;
+        if (!load_scalars(a, n, av) || !load_scalars(b, n, bv) || !Scalar::from_canonical_bytes(r, rr)) return -3;
+        CompressedRistretto c, f, bb; memcpy(c.data(), C, 32); memcpy(f.data(), F, 32); memcpy(bb.data(), B, 32);
+        LinearProof p; ProofError e = LinearProof::create(dev, t, rng, c, rr, av, bv, load_points(G, n), f, bb, p);
+        if (e != ProofError::Ok) return (int)e;
+        std::vector<uint8_t> bytes = p.to_bytes(); memcpy(proof_out, bytes.data(), bytes.size());
+        t.to_wire(transcript);
+        return 0;
+    } catch (const std::exception &) { return -1; }
+}
+int bph_linear_verify(bp_ctx *ctx, uint8_t *transcript, const uint8_t *proof, size_t proof_len, const uint8_t C[32], const uint8_t *G, const uint8_t F[32], const uint8_t B[32],
+                      const uint8_t *b, size_t n) {
+    try {
+        Device dev(ctx); Transcript t(transcript);
+        LinearProof p; ProofError e = LinearProof::from_bytes(proof, proof_len, p);
+        if (e != ProofError::Ok) return (int)e;
+        std::vector<Scalar> bv; if (!load_scalars(b, n, bv)) return -3;
+        CompressedRistretto c, f, bb; memcpy(c.data(), C, 32); memcpy(f.data(), F, 32); memcpy(bb.data(), B, 32);
+        e = p.verify(dev, t, c, load_points(G, n), f, bb, bv);
+        t.to_wire(transcript);
+        return (int)e;
     } catch (const std::exception &) { return -1; }
 }
 static bool load_scalars(const uint8_t *b, size_t n, std::vector<Scalar> &out) { out.resize(n); for (size_t i = 0; i < n; i++) if (!Scalar::from_canonical_bytes(b + 32 * i, out[i])) return false; return true; }

@@ -23,7 +23,7 @@
 namespace bulletproofs {
 
 enum class ProofError { Ok = 0, VerificationError = 1, FormatError = 2, InvalidBitsize = 3, InvalidGeneratorsLength = 4, InvalidAggregation = 5,
-                        WrongNumBlindingFactors = 6, MaliciousDealer = 7 };
+                        WrongNumBlindingFactors = 6, MaliciousDealer = 7, InvalidInputLength = 8 };
 
 using Bytes32 = std::array<uint8_t, 32>;
 using CompressedRistretto = Bytes32;
@@ -119,6 +119,17 @@ struct InnerProductProof {
                       const CompressedRistretto &Q, const std::vector<CompressedRistretto> &G, const std::vector<CompressedRistretto> &H) const;
     std::vector<uint8_t> to_bytes() const;
     static ProofError from_bytes(const uint8_t *s, size_t len, InnerProductProof &out);
+};
+
+// /root/reference/src/linear_proof.rs:27-397 (GHL'21 appendix E.3): proves c = <a, b> for public b and committed a
+struct LinearProof {
+    std::vector<CompressedRistretto> L_vec, R_vec; CompressedRistretto S; Scalar a, r;
+    static ProofError create(Device &dev, Transcript &t, Rng &rng, const CompressedRistretto &C, Scalar r, std::vector<Scalar> a_vec, std::vector<Scalar> b_vec,
+                             const std::vector<CompressedRistretto> &G_vec, const CompressedRistretto &F, const CompressedRistretto &B, LinearProof &out);      // :40-160
+    ProofError verify(Device &dev, Transcript &t, const CompressedRistretto &C, const std::vector<CompressedRistretto> &G, const CompressedRistretto &F,
+                      const CompressedRistretto &B, std::vector<Scalar> b_vec) const;                                                                            // :162-224
+    std::vector<uint8_t> to_bytes() const;                                            // :291-301
+    static ProofError from_bytes(const uint8_t *s, size_t len, LinearProof &out);    // :351-397
 };
 
 struct RangeProof {

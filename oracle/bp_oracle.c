@@ -494,6 +494,116 @@ int orc_ipp_verify(uint8_t *transcript_state, size_t n, const uint8_t *Gf, const
     free(gf); free(hf); free(g); free(h); return rc;
 }
 
+/* ------------------------------------------------------------------ linear_proof.rs (GHL'21 appendix E.3 argument)
+ * LinearProof::create — linear_proof.rs:40-160; verify — :162-224; verification_scalars — :229-270;
+ * subset_product — :272-284; wire format L_0,R_0,..,S,a,r — :291-336, from_bytes :351-397.  Round-trip tests only in the
+ * reference (linear_proof.rs:413-487): parity unpinned. */
+static int linear_create(merlin *t, chacha_rng *rng, const uint8_t C[32], sc r, sc *a, sc *b, ge *G, const ge *F, const ge *B, size_t n, uint8_t *out) {
+    if (!is_pow2(n)) return ORC_FORMAT_ERROR;
+    uint8_t enc[32];
+    t_innerproduct_domain_sep(t, n);
+    t_append_point(t, "C", C);
+    for (size_t i = 0; i < n; i++) t_append_scalar(t, "b_i", &b[i]);
+    for (size_t i = 0; i < n; i++) { ge_encode(enc, &G[i]); t_append_point(t, "G_i", enc); }
+    ge_encode(enc, F); t_append_point(t, "F", enc); ge_encode(enc, B); t_append_point(t, "B", enc);
+    size_t round = 0;
+    sc *ms = malloc(sizeof(sc) * (n + 2)); ge *mp = malloc(sizeof(ge) * (n + 2));
+    while (n != 1) {
+        n /= 2;
+        sc *aL = a, *aR = a + n, *bL = b, *bR = b + n; ge *GL = G, *GR = G + n;
+        sc cL, cR, s_j, t_j; inner_product(&cL, aL, bR, n); inner_product(&cR, aR, bL, n);
+        rng_scalar(rng, &s_j); rng_scalar(rng, &t_j);
+        ge Lp, Rp; uint8_t Lc[32], Rc[32];
+        for (size_t i = 0; i < n; i++) { ms[i] = aL[i]; mp[i] = GR[i]; }
+        ms[n] = s_j; mp[n] = *B; ms[n + 1] = cL; mp[n + 1] = *F;
+        ge_msm_vartime(&Lp, ms, mp, n + 2); ge_encode(Lc, &Lp);
+        for (size_t i = 0; i < n; i++) { ms[i] = aR[i]; mp[i] = GL[i]; }
+        ms[n] = t_j; mp[n] = *B; ms[n + 1] = cR; mp[n + 1] = *F;
+        ge_msm_vartime(&Rp, ms, mp, n + 2); ge_encode(Rc, &Rp);
+        memcpy(out + 64 * round, Lc, 32); memcpy(out + 64 * round + 32, Rc, 32); round++;
+        t_append_point(t, "L", Lc); t_append_point(t, "R", Rc);
+        sc x, xi, tmp; t_challenge_scalar(t, "x_j", &x); sc_invert(&xi, &x);
+        for (size_t i = 0; i < n; i++) {
+            sc_mul(&tmp, &xi, &aR[i]); sc_add(&aL[i], &aL[i], &tmp);
+            sc_mul(&tmp, &x, &bR[i]); sc_add(&bL[i], &bL[i], &tmp);
+            sc s2[2]; sc_one(&s2[0]); s2[1] = x; ge p2[2] = { GL[i], GR[i] }, g; ge_msm_vartime(&g, s2, p2, 2); GL[i] = g;
+        }
+        sc_mul(&tmp, &x, &s_j); sc_add(&r, &r, &tmp); sc_mul(&tmp, &xi, &t_j); sc_add(&r, &r, &tmp);
+    }
+    sc s_star, t_star, tmp; rng_scalar(rng, &s_star); rng_scalar(rng, &t_star);
+    { sc s3[3]; ge p3[3] = { *B, *F, G[0] }, S; s3[0] = t_star; sc_mul(&s3[1], &s_star, &b[0]); s3[2] = s_star; ge_msm_vartime(&S, s3, p3, 3); ge_encode(enc, &S); }
+    memcpy(out + 64 * round, enc, 32);
+    t_append_point(t, "S", enc);
+    sc x_star, a_star, r_star; t_challenge_scalar(t, "x_star", &x_star);
+    sc_mul(&tmp, &x_star, &a[0]); sc_add(&a_star, &s_star, &tmp);
+    sc_mul(&tmp, &x_star, &r); sc_add(&r_star, &t_star, &tmp);
+    sc_tobytes(out + 64 * round + 32, &a_star); sc_tobytes(out + 64 * round + 64, &r_star);
+    free(ms); free(mp);
+    return ORC_OK;
+}
+static int linear_verify(merlin *t, const uint8_t *proof, size_t len, const uint8_t C[32], const ge *G, const ge *F, const ge *B, sc *b, size_t n) {
+    if (len % 32) return ORC_FORMAT_ERROR;
+    size_t ne = len / 32;
+    if (ne < 3 || (ne - 3) % 2) return ORC_FORMAT_ERROR;
+    size_t lg_n = (ne - 3) / 2;
+    if (lg_n >= 32) return ORC_FORMAT_ERROR;
+    const uint8_t *S = proof + 64 * lg_n; sc pa, pr;
+    if (!sc_from_canonical(&pa, S + 32) || !sc_from_canonical(&pr, S + 64)) return ORC_FORMAT_ERROR;
+    uint8_t enc[32];
+    t_innerproduct_domain_sep(t, n);
+    t_append_point(t, "C", C);
+    for (size_t i = 0; i < n; i++) t_append_scalar(t, "b_i", &b[i]);
+    for (size_t i = 0; i < n; i++) { ge_encode(enc, &G[i]); t_append_point(t, "G_i", enc); }
+    ge_encode(enc, F); t_append_point(t, "F", enc); ge_encode(enc, B); t_append_point(t, "B", enc);
+    if (n != ((size_t)1 << lg_n)) return ORC_VERIFICATION_ERROR;
+    sc x[32], xi[32], tmp; size_t nm = n;
+    for (size_t j = 0; j < lg_n; j++) {
+        if (t_validate_and_append_point(t, "L", proof + 64 * j) || t_validate_and_append_point(t, "R", proof + 64 * j + 32)) return ORC_VERIFICATION_ERROR;
+        t_challenge_scalar(t, "x_j", &x[j]);
+        nm /= 2;
+        for (size_t i = 0; i < nm; i++) { sc_mul(&tmp, &x[j], &b[nm + i]); sc_add(&b[i], &b[i], &tmp); }
+    }
+    for (size_t j = 0; j < lg_n; j++) sc_invert(&xi[j], &x[j]);
+    t_append_point(t, "S", S);
+    sc x_star; t_challenge_scalar(t, "x_star", &x_star);
+    size_t nt = 3 + 2 * lg_n + n, q = 0; int bad = 0;
+    sc *ms = malloc(sizeof(sc) * nt); ge *mp = malloc(sizeof(ge) * nt);
+    ms[q] = pr; mp[q++] = *B;
+    sc_mul(&ms[q], &pa, &b[0]); mp[q++] = *F;
+    sc_neg(&ms[q], &x_star); bad |= !ge_decode(&mp[q++], C);
+    for (size_t j = 0; j < lg_n; j++) { sc_mul(&tmp, &x_star, &x[j]); sc_neg(&ms[q], &tmp); bad |= !ge_decode(&mp[q++], proof + 64 * j); }
+    for (size_t j = 0; j < lg_n; j++) { sc_mul(&tmp, &x_star, &xi[j]); sc_neg(&ms[q], &tmp); bad |= !ge_decode(&mp[q++], proof + 64 * j + 32); }
+    sc *s = malloc(sizeof(sc) * n); sc_one(&s[0]);
+    for (size_t i = 1; i < n; i++) { int lg_i = 63 - __builtin_clzll((unsigned long long)i); sc_mul(&s[i], &s[i - ((size_t)1 << lg_i)], &x[(lg_n - 1) - lg_i]); }
+    for (size_t i = 0; i < n; i++) { sc_mul(&ms[q], &pa, &s[i]); mp[q++] = G[i]; }
+    ge Sp, expect; bad |= !ge_decode(&Sp, S);
+    int rc = ORC_OK;
+    if (bad) rc = ORC_VERIFICATION_ERROR;
+    else { ge_msm_vartime(&expect, ms, mp, nt); if (!ge_ristretto_eq(&expect, &Sp)) rc = ORC_VERIFICATION_ERROR; }
+    free(ms); free(mp); free(s);
+    return rc;
+}
+/* compressed-input wrappers: G = n points, F, B; a, b = n scalars; rng = ChaChaRng::from_seed(seed) */
+int orc_linear_create(uint8_t *tstate, const uint8_t seed[32], const uint8_t C[32], const uint8_t r[32], const uint8_t *a, const uint8_t *b, const uint8_t *G,
+                      const uint8_t F[32], const uint8_t B[32], size_t n, uint8_t *out) {
+    ge_init_constants();
+    merlin t; memcpy(&t, tstate, sizeof t); chacha_rng rng; chacha_seed(&rng, seed);
+    sc rr, *av = malloc(sizeof(sc) * n), *bv = malloc(sizeof(sc) * n); ge *g = malloc(sizeof(ge) * n), f, bb; int rc = ORC_OK;
+    if (!sc_from_canonical(&rr, r) || !ge_decode(&f, F) || !ge_decode(&bb, B)) rc = ORC_FORMAT_ERROR;
+    for (size_t i = 0; i < n && !rc; i++) if (!sc_from_canonical(&av[i], a + 32 * i) || !sc_from_canonical(&bv[i], b + 32 * i) || !ge_decode(&g[i], G + 32 * i)) rc = ORC_FORMAT_ERROR;
+    if (!rc) { rc = linear_create(&t, &rng, C, rr, av, bv, g, &f, &bb, n, out); memcpy(tstate, &t, sizeof t); }
+    free(av); free(bv); free(g); return rc;
+}
+int orc_linear_verify(uint8_t *tstate, const uint8_t *proof, size_t len, const uint8_t C[32], const uint8_t *G, const uint8_t F[32], const uint8_t B[32], const uint8_t *b, size_t n) {
+    ge_init_constants();
+    merlin t; memcpy(&t, tstate, sizeof t);
+    sc *bv = malloc(sizeof(sc) * (n ? n : 1)); ge *g = malloc(sizeof(ge) * (n ? n : 1)), f, bb; int rc = ORC_OK;
+    if (!ge_decode(&f, F) || !ge_decode(&bb, B)) rc = ORC_FORMAT_ERROR;
+    for (size_t i = 0; i < n && !rc; i++) if (!sc_from_canonical(&bv[i], b + 32 * i) || !ge_decode(&g[i], G + 32 * i)) rc = ORC_FORMAT_ERROR;
+    if (!rc) { rc = linear_verify(&t, proof, len, C, g, &f, &bb, bv, n); memcpy(tstate, &t, sizeof t); }
+    free(bv); free(g); return rc;
+}
+
 /* ------------------------------------------------------------------ R1CS (prover.rs / verifier.rs) with three gadgets */
 #include "r1cs.h"
 

@@ -37,6 +37,8 @@ class Oracle:
         L.orc_shake256.argtypes = [_p, _sz, _p, _sz]
         L.orc_ipp_create.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]
         L.orc_ipp_verify.argtypes = [_p, _sz, _p, _p, _p, _p, _p, _p, _p, _sz]
+        L.orc_linear_create.argtypes = [_p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]
+        L.orc_linear_verify.argtypes = [_p, _p, _sz, _p, _p, _p, _p, _p, _sz]
         L.orc_r1cs_prove.argtypes = [_vp, _p, ctypes.c_int, _p, _p, _sz, ctypes.c_uint64, ctypes.c_uint64, _p, _p, ctypes.POINTER(_sz), _p]
         L.orc_r1cs_verify.argtypes = [_vp, _p, ctypes.c_int, _p, _sz, ctypes.c_uint64, _p, _sz, _p]
         L.orc_init()
@@ -152,6 +154,17 @@ class Oracle:
         o = ctypes.create_string_buffer(64)
         self.L.orc_sha3_512(data, len(data), o)
         return o.raw
+
+    # LinearProof
+    def linear_create(self, tstate, seed, C, r, a, b, G, F, B):
+        n = len(a) // 32
+        st = ctypes.create_string_buffer(tstate, 256); out = ctypes.create_string_buffer(32 * (2 * (n.bit_length() - 1) + 3))
+        rc = self.L.orc_linear_create(st, seed, C, r, a, b, G, F, B, n, out)
+        return rc, st.raw, out.raw
+
+    def linear_verify(self, tstate, proof, C, G, F, B, b):
+        st = ctypes.create_string_buffer(tstate, 256)
+        return self.L.orc_linear_verify(st, proof, len(proof), C, G, F, B, b, len(b) // 32)
 
     # R1CS (gadget 0 shuffle, 1 example, 2 range)
     def r1cs_prove(self, g, tstate, gadget, values, blindings, param=0, aux=0, ext_seed=bytes(32)):

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *__restrict__
     }
 }
 // pass 4: bucket accumulation, one thread per bucket: sum of +-points listed in its slice (mixed additions)
-__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
+__global__ void __launch_bounds__(128, 5) k_msm_accumulate(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
                                                         const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, int W, uint32_t nb, size_t n_buckets,
                                                         const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,
                                                         ge_ext *__restrict__ buckets) {
@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(128) k_rp_scalars(rp_geom g, const rp_head *__
     }
 }
 // decompress the per-proof points in MSM order A,S,T_1,T_2,L..,R..,V.. straight out of the proof bytes
-__global__ void __launch_bounds__(128) k_rp_decompress(const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ commitments, rp_geom g, uint32_t count,
+__global__ void __launch_bounds__(128, 5) k_rp_decompress(const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ commitments, rp_geom g, uint32_t count,
                                                        ge_niels *__restrict__ out, uint32_t *__restrict__ status) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)count * g.D) return;

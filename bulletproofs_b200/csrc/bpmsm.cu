@@ -30,9 +30,9 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum KernelId { KID_DECOMPRESS, KID_COMPRESS, KID_FROM_UNIFORM, KID_MSM_COUNT, KID_MSM_SCAN, KID_MSM_SCATTER, KID_MSM_ACCUMULATE, KID_MSM_REDUCE,
+enum KernelId { KID_DECOMPRESS, KID_COMPRESS, KID_FROM_UNIFORM, KID_MSM_COUNT, KID_MSM_SCAN, KID_MSM_SCATTER, KID_MSM_ACCUMULATE, KID_MSM_ACC_HEAVY, KID_MSM_REDUCE,
                 KID_MSM_COMBINE, KID_RP_TRANSCRIPT, KID_RP_SCALARS, KID_RP_DECOMPRESS, KID_RP_STATIC_REDUCE, KID_IPP_FOLD, KID_SMALL, KID_COUNT };
-const char *const KERNEL_NAMES[KID_COUNT] = {"k_decompress", "k_compress", "k_from_uniform", "k_msm_count", "k_msm_scan", "k_msm_scatter", "k_msm_accumulate",
+const char *const KERNEL_NAMES[KID_COUNT] = {"k_decompress", "k_compress", "k_from_uniform", "k_msm_count", "k_msm_scan", "k_msm_scatter", "k_msm_accumulate", "k_msm_accumulate_heavy",
                                              "k_msm_reduce", "k_msm_combine", "k_rp_transcript", "k_rp_scalars", "k_rp_decompress", "k_rp_static_reduce", "k_ipp_fold", "small_kernels"};
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
@@ -109,18 +109,25 @@ int msm_core(bp_ctx *ctx, const MsmArgs &a, ge_ext *d_results) {
     uint32_t nb = 1u << (c - 1);
     size_t segs = (size_t)a.n_msm * W, n_buckets = segs * nb;
     // counts | size histogram | bin cursors share one allocation so a single memset clears them
-    CK(ctx, ctx->counts.ensure((n_buckets + 2 * MSM_SIZE_BINS) * 4)); CK(ctx, ctx->starts.ensure(n_buckets * 4)); CK(ctx, ctx->cursor.ensure(n_buckets * 4));
-    CK(ctx, ctx->order.ensure(n_buckets * 4));
-    uint32_t *size_hist = ctx->counts.as<uint32_t>() + n_buckets, *bin_cursor = size_hist + MSM_SIZE_BINS;
+    CK(ctx, ctx->counts.ensure((n_buckets + 2 * MSM_SIZE_BINS + 4) * 4)); CK(ctx, ctx->starts.ensure(n_buckets * 4)); CK(ctx, ctx->cursor.ensure(n_buckets * 4));
+    // heavy-bucket threshold: far above the mean bucket size, and large enough that a block per bucket pays off.
+    // A bucket holds >= heavy_min entries, so at most T*W/heavy_min of them exist.
+    uint32_t heavy_min = (uint32_t)std::max<size_t>(256, 8 * (avg / nb + 1));
+    size_t heavy_cap = std::min<size_t>(n_buckets, (size_t)a.T * W / heavy_min + 1);
+    CK(ctx, ctx->order.ensure((n_buckets + heavy_cap) * 4));
+    uint32_t *size_hist = ctx->counts.as<uint32_t>() + n_buckets, *bin_cursor = size_hist + MSM_SIZE_BINS, *heavy_n = bin_cursor + MSM_SIZE_BINS;
+    uint32_t *heavy = ctx->order.as<uint32_t>() + n_buckets;
     CK(ctx, ctx->sorted.ensure((size_t)a.T * W * 4)); CK(ctx, ctx->buckets.ensure(n_buckets * sizeof(ge_ext))); CK(ctx, ctx->wsums.ensure(segs * sizeof(ge_ext)));
     cudaStream_t s = ctx->stream;
-    CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, (n_buckets + 2 * MSM_SIZE_BINS) * 4, s));
+    CK(ctx, cudaMemsetAsync(ctx->counts.p, 0, (n_buckets + 2 * MSM_SIZE_BINS + 4) * 4, s));
     LAUNCH(ctx, KID_MSM_COUNT, k_msm_count<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->counts.as<uint32_t>(), a.d_err));
     LAUNCH(ctx, KID_MSM_SCAN, k_msm_scan<<<(unsigned)segs, 256, 0, s>>>(ctx->counts.as<uint32_t>(), nb, ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), size_hist));
-    LAUNCH(ctx, KID_MSM_SCAN, k_msm_order<<<blocks_for(n_buckets, 256), 256, 0, s>>>(ctx->counts.as<uint32_t>(), n_buckets, size_hist, bin_cursor, ctx->order.as<uint32_t>()));
+    LAUNCH(ctx, KID_MSM_SCAN, k_msm_order<<<blocks_for(n_buckets, 256), 256, 0, s>>>(ctx->counts.as<uint32_t>(), n_buckets, size_hist, bin_cursor, ctx->order.as<uint32_t>(), heavy_min, heavy_n, heavy));
     LAUNCH(ctx, KID_MSM_SCATTER, k_msm_scatter<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>()));
     LAUNCH(ctx, KID_MSM_ACCUMULATE, k_msm_accumulate<<<blocks_for(n_buckets, 128), 128, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(), a.d_offsets, ctx->order.as<uint32_t>(), W, nb,
-                                                                n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>()));
+                                                                n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>(), heavy_min));
+    LAUNCH(ctx, KID_MSM_ACC_HEAVY, k_msm_accumulate_heavy<<<(unsigned)std::min<size_t>(heavy_cap, 2 * 148), MSM_HEAVY_THREADS, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(),
+                                                                a.d_offsets, heavy_n, heavy, W, nb, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>()));
     unsigned rthreads = nb >= 64 ? 64 : 32;      // two warps per segment: fewer scan/tree additions per useful bucket addition
     LAUNCH(ctx, KID_MSM_REDUCE, k_msm_reduce<<<(unsigned)segs, rthreads, 0, s>>>(ctx->buckets.as<ge_ext>(), nb, ctx->wsums.as<ge_ext>()));
     if (a.n_msm <= 256)      // few MSMs: the Horner chain is pure latency -> four cooperating lanes per MSM

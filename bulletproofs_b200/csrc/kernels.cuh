@@ -140,7 +140,14 @@ __global__ void __launch_bounds__(128) k_niels_to_compressed(const ge_niels *__r
 // ------------------------------------------------------------------ K2: Pippenger bucket pipeline
 // A batch of n_msm MSMs over a flat term array.  "segment" = (msm, window); every segment owns nb =
 // 2^(c-1) buckets and a slice of `sorted` with room for all terms of its MSM:
-//     seg = msm*W + w,   slice base = W*offsets[msm] + w*(offsets[msm+1]-offsets[msm]).
+//     seg = msm*W + w,   slice base = W*offsets[msm] + w*len,  len = offsets[msm+1]-offsets[msm].
+// Buckets are accumulated by one thread each, except "heavy" ones (size >= heavy_min, chosen by the host as a multiple
+// of the mean bucket size): k_msm_order lists those and k_msm_accumulate_heavy gives each a whole block.  Heavy buckets
+// are not an adversarial corner only: scalars are < l ~ 2^252, so when c*(W-1) = 252 (c = 9, 12, ...) the top window
+// holds nothing but the recoding carry and HALF of all terms land in its bucket 0.
+__device__ __forceinline__ size_t msm_slice_base(uint32_t o0, uint32_t len, uint32_t w, int W) {
+    return (size_t)W * (size_t)o0 + (size_t)w * (size_t)len;
+}
 __device__ __forceinline__ uint32_t msm_of_term(const uint32_t *__restrict__ offsets, uint32_t n_msm, uint32_t t) {
     uint32_t lo = 0, hi = n_msm;            // largest j with offsets[j] <= t
     while (hi - lo > 1) { uint32_t mid = (lo + hi) >> 1; if (__ldg(offsets + mid) <= t) lo = mid; else hi = mid; }
@@ -197,7 +204,8 @@ __global__ void __launch_bounds__(256) k_msm_scan(const uint32_t *__restrict__ c
 // load-balancing order: bucket ids sorted by decreasing size (counting sort over the size histogram), so that the 32
 // buckets a warp accumulates have (nearly) equal lengths and the longest buckets start first
 __global__ void __launch_bounds__(256) k_msm_order(const uint32_t *__restrict__ counts, size_t n_buckets, const uint32_t *__restrict__ size_hist,
-                                                   uint32_t *__restrict__ bin_cursor, uint32_t *__restrict__ order) {
+                                                   uint32_t *__restrict__ bin_cursor, uint32_t *__restrict__ order, uint32_t heavy_min,
+                                                   uint32_t *__restrict__ heavy_n, uint32_t *__restrict__ heavy) {
     __shared__ uint32_t base[MSM_SIZE_BINS];
     __shared__ uint32_t wsum[8];
     {   // exclusive scan of the 256-bin histogram, redundantly per block
@@ -211,8 +219,10 @@ __global__ void __launch_bounds__(256) k_msm_order(const uint32_t *__restrict__ 
     }
     size_t gb = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gb >= n_buckets) return;
-    uint32_t bin = MSM_SIZE_BINS - 1 - min(counts[gb], (uint32_t)MSM_SIZE_BINS - 1);
+    uint32_t cnt = counts[gb];
+    uint32_t bin = MSM_SIZE_BINS - 1 - min(cnt, (uint32_t)MSM_SIZE_BINS - 1);
     order[base[bin] + atomicAdd(bin_cursor + bin, 1u)] = (uint32_t)gb;
+    if (cnt >= heavy_min) heavy[atomicAdd(heavy_n, 1u)] = (uint32_t)gb;
 }
 // pass 3: scatter term ids (sign in bit 31) into their bucket's slice
 __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *__restrict__ scalars, const uint32_t *__restrict__ offsets, uint32_t n_msm, uint32_t T,
@@ -234,21 +244,22 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *__restrict__
         if (d == 0) continue;
         uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
         uint32_t pos = atomicAdd(cursor + ((size_t)msm * W + w) * nb + b, 1u);
-        sorted[(size_t)W * o0 + (size_t)w * len + pos] = t | (d < 0 ? 0x80000000u : 0u);
+        sorted[msm_slice_base(o0, len, (uint32_t)w, W) + pos] = t | (d < 0 ? 0x80000000u : 0u);
     }
 }
 // pass 4: bucket accumulation, one thread per bucket: sum of +-points listed in its slice (mixed additions)
 __global__ void __launch_bounds__(128, 5) k_msm_accumulate(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
                                                         const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, int W, uint32_t nb, size_t n_buckets,
                                                         const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,
-                                                        ge_ext *__restrict__ buckets) {
+                                                        ge_ext *__restrict__ buckets, uint32_t heavy_min) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (tid >= n_buckets) return;
     size_t gb = order[tid];
     size_t seg = gb / nb; uint32_t msm = (uint32_t)(seg / W), w = (uint32_t)(seg % W);
     uint32_t o0 = __ldg(offsets + msm), len = __ldg(offsets + msm + 1) - o0;
-    const uint32_t *slice = sorted + (size_t)W * o0 + (size_t)w * len;
+    const uint32_t *slice = sorted + msm_slice_base(o0, len, w, W);
     uint32_t lo = starts[gb], hi = ends[gb];
+    if (hi - lo >= heavy_min) return;           // k_msm_accumulate_heavy owns this bucket
     ge_ext acc = ge_identity();
     for (uint32_t e = lo; e < hi; e++) {
         uint32_t v = __ldg(slice + e), t = v & 0x7fffffffu;
@@ -259,6 +270,43 @@ __global__ void __launch_bounds__(128, 5) k_msm_accumulate(const uint32_t *__res
         acc = ge_madd(acc, q);
     }
     st_ext(buckets + gb, acc);
+}
+// pass 4b: heavy buckets, one block per bucket (grid-stride over the list k_msm_order built): threads take strided
+// entries, then a shuffle tree + one shared-memory round add the partial sums
+#define MSM_HEAVY_THREADS 512
+__global__ void __launch_bounds__(MSM_HEAVY_THREADS) k_msm_accumulate_heavy(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
+                                                        const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ heavy_n, const uint32_t *__restrict__ heavy, int W, uint32_t nb,
+                                                        const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,
+                                                        ge_ext *__restrict__ buckets) {
+    __shared__ ge_ext sm[MSM_HEAVY_THREADS / 32];
+    uint32_t n_heavy = *heavy_n, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
+        size_t gb = heavy[h];
+        size_t seg = gb / nb; uint32_t msm = (uint32_t)(seg / W), w = (uint32_t)(seg % W);
+        uint32_t o0 = __ldg(offsets + msm), len = __ldg(offsets + msm + 1) - o0;
+        const uint32_t *slice = sorted + msm_slice_base(o0, len, w, W);
+        uint32_t lo = starts[gb], hi = ends[gb];
+        ge_ext acc = ge_identity();
+        for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+            uint32_t v = __ldg(slice + e), t = v & 0x7fffffffu;
+            uint32_t pi = point_idx ? __ldg(point_idx + t) : (t | BP_POINT_DYNAMIC);
+            const ge_niels *src = (pi & BP_POINT_DYNAMIC) ? pts_dynamic + (pi & 0x7fffffffu) : pts_static + pi;
+            ge_niels q = ldg_niels(src);
+            if (v & 0x80000000u) q = ge_niels_neg(q);
+            acc = ge_madd(acc, q);
+        }
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) { ge_ext o = shfl_down_ext(acc, d); acc = ge_add(acc, o); }
+        if (lane == 0) sm[wid] = acc;
+        __syncthreads();
+        if (wid == 0) {
+            ge_ext r = lane < (blockDim.x >> 5) ? sm[lane] : ge_identity();
+#pragma unroll 1
+            for (int d = 16; d >= 1; d >>= 1) { ge_ext o = shfl_down_ext(r, d); r = ge_add(r, o); }
+            if (lane == 0) st_ext(buckets + gb, r);
+        }
+        __syncthreads();
+    }
 }
 // pass 5: bucket reduction  R = sum_j (j+1) B_j  per segment, one block per segment.
 // Each thread owns a contiguous chunk; a warp-shuffle suffix scan over the chunk sums gives every

@@ -73,8 +73,14 @@ BP_HDN void rp_transcript(rp_challenges &ch, const uint8_t *proof, uint32_t k, c
         merlin_append(t, "L", LR + 64 * j, 32); merlin_append(t, "R", LR + 64 * j + 32, 32);
         ch.u[j] = rp_challenge(t, "u");
     }
+    // The device multiplies the proof's check by lambda = (prod u_j)^2 y^(N-1) (see the header).  A zero challenge would make
+    // lambda vanish and the proof drop out of the combination, so it is rejected outright; the reference cannot verify such a
+    // transcript either (u_j = 0 has no inverse), and an honest or dishonest prover hits it with probability ~2^-252 per hash.
+    for (uint32_t j = 0; j < k; j++) bad = bad || sc_is_zero(ch.u[j]);
+    bad = bad || sc_is_zero(ch.y);
     if (bad) { ch.status = BP_PROOF_VERIFICATION_ERROR; return; }
     ch.c = rp_wide(weights); ch.rho = rp_wide(weights + 64);
+    if (sc_is_zero(ch.rho)) ch.rho = sc_mont_one();                  // a zero weight (probability 2^-252) would skip the proof
 }
 
 struct rp_head {                // Montgomery form; "L" = Lambda = rho * lambda

@@ -100,6 +100,24 @@ def test_msm_edge_cases(gpu_ctx, orc):
     assert gpu_ctx.msm(le(l), pts[0])[0] == bp.ERR_NONCANONICAL_SCALAR
 
 
+@pytest.mark.parametrize("n,kind", [(4096, "uniform"), (5000, "equal"), (12290, "few"), (1 << 16, "uniform")])
+def test_msm_heavy_buckets(gpu_ctx, orc, n, kind):
+    """Buckets far above the mean size go through k_msm_accumulate_heavy (a block per bucket).  With uniform scalars
+    < l and c*(W-1) = 252 half of all terms share the top window's bucket 0; equal / few distinct scalars put every
+    term of a window in one or a handful of buckets."""
+    rnd = random.Random(n)
+    base = [orc.from_uniform(rnd.randbytes(64)) for _ in range(64)]
+    if kind == "uniform":
+        sc = b"".join(le(rnd.randrange(l)) for _ in range(n))
+    elif kind == "equal":
+        sc = le(rnd.randrange(l)) * n
+    else:
+        few = [le(rnd.randrange(l)) for _ in range(3)]
+        sc = b"".join(rnd.choice(few) for _ in range(n))
+    pp = b"".join(rnd.choice(base) for _ in range(n))
+    assert gpu_ctx.msm(sc, pp) == orc.msm(sc, pp)
+
+
 def test_msm_batch_ragged(gpu_ctx, orc):
     rnd = random.Random(10)
     base = [orc.from_uniform(rnd.randbytes(64)) for _ in range(32)]
@@ -209,4 +227,36 @@ def test_full_size_batch_properties(gpu_ctx, orc):
         i = rnd.randrange(1024); pb = bytearray(big_p); pb[i * plen + rnd.randrange(plen)] ^= 2
         got = bp.verify_batch(gpu_ctx, gens, t, bytes(pb), big_v, 64, 1, 1024)
         assert [j for j, v in enumerate(got) if v] == [i]
+    gens.close()
+
+
+def test_differential_fuzz_against_oracle(gpu_ctx, orc):
+    """Many random mutations of valid proofs (bit flips, byte stomps, swapped fields, swapped proofs, zeroed / maximal
+    fields, commitments of other proofs) in batches: the GPU verdict list must equal the oracle's per-proof verdicts."""
+    import bulletproofs_b200 as bp
+    label = b"fuzz"
+    n, m, count = 16, 2, 48
+    og = orc.gens(16, 2); gens = bp.Gens(gpu_ctx, 16, 2)
+    proofs, Vs = _workload(orc, og, label, n, m, count, seed=999)
+    plen = len(proofs) // count
+    t = bp.Transcript(label); ot = orc.transcript(label)
+    rnd = random.Random(2024)
+    for round_ in range(6):
+        pb, vb = bytearray(proofs), bytearray(Vs)
+        for i in rnd.sample(range(count), 20):
+            kind = rnd.randrange(9); o = i * plen
+            if kind == 0: pb[o + rnd.randrange(plen)] ^= 1 << rnd.randrange(8)
+            elif kind == 1: pb[o + rnd.randrange(plen)] = rnd.randrange(256)
+            elif kind == 2:                                           # swap two 32-byte fields of the proof
+                a, b = rnd.sample(range(plen // 32), 2); pb[o + 32 * a:o + 32 * a + 32], pb[o + 32 * b:o + 32 * b + 32] = pb[o + 32 * b:o + 32 * b + 32], pb[o + 32 * a:o + 32 * a + 32]
+            elif kind == 3:                                           # another proof's bytes with this proof's commitments
+                j = rnd.randrange(count); pb[o:o + plen] = proofs[j * plen:(j + 1) * plen]
+            elif kind == 4: f = rnd.randrange(plen // 32); pb[o + 32 * f:o + 32 * f + 32] = bytes(32)
+            elif kind == 5: f = rnd.randrange(plen // 32); pb[o + 32 * f:o + 32 * f + 32] = bytes([255]) * 32
+            elif kind == 6: vb[i * 32 * m + rnd.randrange(32 * m)] ^= 1 << rnd.randrange(8)
+            elif kind == 7: f = rnd.randrange(plen // 32); pb[o + 32 * f:o + 32 * f + 32] = le(l - 1)      # canonical-boundary scalar / non-point
+            else: f = rnd.randrange(plen // 32); pb[o + 32 * f:o + 32 * f + 32] = le(p - 1)                 # largest field element
+        want = orc.verify_many(og, ot, bytes(pb), plen, bytes(vb), n, m, count)
+        got = bp.verify_batch(gpu_ctx, gens, t, bytes(pb), bytes(vb), n, m, count, seed=bytes([round_]) * 32)
+        assert got == want, (round_, [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w])
     gens.close()

@@ -122,30 +122,31 @@ def run_reference(args, rank, world):
     plen = len(proofs) // BATCH
     t = orc.transcript(LABEL)
     probe = min(BATCH, 8 * cores)
-    t0 = time.perf_counter(); st = orc.verify_many(og, t, proofs[:probe * plen], plen, Vs[:probe * 32], N_BITS, M_PARTIES, probe, nthreads=cores); dt = time.perf_counter() - t0
+    t0 = time.perf_counter(); st = orc.verify_many(og, t, proofs[:probe * plen], plen, Vs[:probe * 32 * M_PARTIES], N_BITS, M_PARTIES, probe, nthreads=cores); dt = time.perf_counter() - t0
     assert not any(st)
     rate = probe / dt
     budget_s = 90.0
     sample = int(max(cores, min(BATCH, rate * budget_s / max(1, args.steps + args.warmup))))
     for _ in range(args.warmup):
-        orc.verify_many(og, t, proofs[:sample * plen], plen, Vs[:sample * 32], N_BITS, M_PARTIES, sample, nthreads=cores)
+        orc.verify_many(og, t, proofs[:sample * plen], plen, Vs[:sample * 32 * M_PARTIES], N_BITS, M_PARTIES, sample, nthreads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        st = orc.verify_many(og, t, proofs[:sample * plen], plen, Vs[:sample * 32], N_BITS, M_PARTIES, sample, nthreads=cores)
+        st = orc.verify_many(og, t, proofs[:sample * plen], plen, Vs[:sample * 32 * M_PARTIES], N_BITS, M_PARTIES, sample, nthreads=cores)
     dt = time.perf_counter() - t0
     assert not any(st)
     value = sample * args.steps / dt
     cpu = {"value": value, "unit": "proofs/s", "cores": cores, "kind": "port",
-           "sample": f"{sample} of the {BATCH} (64,1) proofs per step, per-proof verify_multiple (Straus, 147 terms), one proof per task on {cores} threads"}
+           "sample": f"{sample} of the {BATCH} (64,{M_PARTIES}) proofs per step, per-proof verify_multiple ({2 * N_BITS * M_PARTIES + 2 * (N_BITS * M_PARTIES).bit_length() - 2 + M_PARTIES + 6} terms), one proof per task on {cores} threads"}
     print(json.dumps({"impl": "reference", "metric": "64-bit rangeproof verifications/sec (batched)", "value": value, "unit": "proofs/s", "n_gpus": 0,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
                       "vs_baseline": None, "dtype": "u64 (51-bit limbs, CPU)", "data": "synthetic",
-                      "config": {"workload": f"batched verify of {BATCH}x 64-bit RangeProofs (m=1) per GPU", "n": N_BITS, "m": M_PARTIES, "batch": BATCH,
+                      "config": {"workload": f"batched verify of {BATCH}x 64-bit RangeProofs (m={M_PARTIES}) per GPU", "n": N_BITS, "m": M_PARTIES, "batch": BATCH,
                                  "reference_sample": f"{sample} proofs per step on {cores} host threads"},
                       "cpu_baseline": cpu, "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 def main():
+    global M_PARTIES, BATCH
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)
@@ -154,7 +155,10 @@ def main():
     ap.add_argument("--streams", type=int, default=24)
     ap.add_argument("--threads", type=int, default=1, help="host threads issuing steps (each drives streams/threads contexts)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--m", type=int, default=M_PARTIES, help="parties per proof (BASELINE config 3: --m 16 --batch 256); the bench line is the default")
+    ap.add_argument("--batch", type=int, default=BATCH, help="proofs per verified batch")
     args = ap.parse_args()
+    M_PARTIES, BATCH = args.m, args.batch
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
@@ -339,7 +343,7 @@ def main():
     out = {"metric": "64-bit rangeproof verifications/sec (batched)", "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32x8 (mod 2^255-19) / u32x8 (mod l)",
            "data": "synthetic (oracle-proved valid proofs over uniform 64-bit values)",
-           "config": {"workload": f"batched verify of {BATCH}x 64-bit RangeProofs (m=1) per GPU", "n": N_BITS, "m": M_PARTIES, "batch": BATCH, "streams": S, "host_threads": NT, "host_issue_ms_per_step": round(1e3 * host_issue_dev / args.steps, 4),
+           "config": {"workload": f"batched verify of {BATCH}x 64-bit RangeProofs (m={M_PARTIES}) per GPU", "n": N_BITS, "m": M_PARTIES, "batch": BATCH, "streams": S, "host_threads": NT, "host_issue_ms_per_step": round(1e3 * host_issue_dev / args.steps, 4),
                       "l2": f"inputs larger than L2: pool of {P} distinct input batches ({P * batch_bytes >> 20} MiB) cycled", "parallelism": f"independent batches per GPU x{world}"},
            "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": max(ms_e2e, wall_e2e * 1e3) / args.steps},
            "gpu_launches": launches, "clocks": clocks, "roofline": roofline}

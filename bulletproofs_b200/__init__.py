@@ -50,6 +50,7 @@ SYMBOLS = {
     "bp_prof_kernel_count": (_int, []),
     "bp_prof_kernel_name": (_c.c_char_p, [_int]),
     "bp_prof_report": (_int, [_vp, _c.POINTER(_c.c_double), _c.POINTER(_c.c_uint64)]),
+    "bp_prof_timeline": (_int, [_vp, _vp, _c.POINTER(_c.c_int), _c.POINTER(_c.c_double), _c.POINTER(_c.c_double), _c.c_size_t, _c.POINTER(_c.c_size_t)]),
     "bp_transcript_new": (None, [_u8p, _sz, _u8p]),
     "bp_transcript_append_message": (None, [_u8p, _u8p, _u8p, _sz]),
     "bp_transcript_append_u64": (None, [_u8p, _u8p, _c.c_uint64]),
@@ -209,6 +210,12 @@ class Context:
         return {lib().bp_prof_kernel_name(i).decode(): (ms[i], cnt[i]) for i in range(n) if cnt[i]}
 
     # ---- group primitives
+    def prof_timeline(self, ref: "Context", cap: int = 65536):
+        """[(kernel name, start ms, end ms)] of every launch recorded since prof_enable, relative to ref's first record."""
+        ids = (ctypes.c_int * cap)(); a = (ctypes.c_double * cap)(); b = (ctypes.c_double * cap)(); n = ctypes.c_size_t(0)
+        self._check(lib().bp_prof_timeline(self._h, ref._h, ids, a, b, cap, ctypes.byref(n)))
+        return [(lib().bp_prof_kernel_name(ids[i]).decode(), a[i], b[i]) for i in range(n.value)]
+
     def decompress_check(self, points: bytes):
         n = len(points) // 32
         ok = ctypes.create_string_buffer(max(n, 1))

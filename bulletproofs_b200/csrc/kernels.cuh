@@ -448,24 +448,109 @@ struct rp_geom { uint32_t n, m, k, N, D, S; uint32_t proof_len; };   // D = 4+2k
 #define RP_TR_THREADS 32
 __global__ void __launch_bounds__(RP_TR_THREADS) k_rp_transcript(const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ commitments, rp_geom g,
                                                                    const uint8_t *__restrict__ tstate, const uint8_t *__restrict__ seed, uint32_t count,
-                                                                   rp_head *__restrict__ heads, sc *__restrict__ tabs, const sc *__restrict__ pow2, uint32_t *__restrict__ status) {
+                                                                   uint8_t *__restrict__ raw, uint32_t *__restrict__ status) {
     __shared__ __align__(16) uint8_t rows[RP_TR_THREADS][204];
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= count) return;
     const uint8_t *proof = proofs + (size_t)p * g.proof_len, *V = commitments + (size_t)p * g.m * 32;
+    uint8_t (*my)[64] = reinterpret_cast<uint8_t (*)[64]>(raw + (size_t)p * (RP_RAW_U + g.k) * 64);
     // per-proof batching weights: Keccak-f PRF keyed by the 32-byte seed, domain-separated by the proof index
     uint64_t st[25];
     for (int i = 0; i < 25; i++) st[i] = 0;
     for (int i = 0; i < 4; i++) { uint64_t wv = 0; for (int j = 0; j < 8; j++) wv |= (uint64_t)seed[8 * i + j] << (8 * j); st[i] = wv; }
     st[4] = p; st[5] = 0x62702d7765696768ULL;  /* "bp-weigh" */ st[16] ^= 0x8000000000000000ULL;
     keccak_f1600(st);
-    uint8_t weights[128];
-    for (int i = 0; i < 16; i++) for (int j = 0; j < 8; j++) weights[8 * i + j] = (uint8_t)(st[i] >> (8 * j));
-    rp_challenges ch;
-    rp_transcript(ch, proof, g.k, V, g.n, g.m, tstate, weights, rows[threadIdx.x]);
-    status[p] = ch.status;
-    heads[p].status = ch.status;
-    if (ch.status == BP_PROOF_OK) rp_scalars_head(heads[p], tabs + (size_t)p * rp_tab_size(g.k, g.m), pow2, ch, proof, g.k, g.n, g.m);
+    uint64_t *wout = reinterpret_cast<uint64_t *>(my[RP_RAW_C]);      // c = wide(st[0..8)), rho = wide(st[8..16)); rows are 64-byte aligned
+    for (int i = 0; i < 16; i++) wout[i] = st[i];
+    status[p] = rp_transcript_raw(my, proof, g.k, V, g.n, g.m, tstate, rows[threadIdx.x]);
+}
+// Cooperative head: the ~180 Montgomery products of one proof's shared scalars and tables (rp_scalars_head is the sequential
+// statement of the same values) are split over RP_HEAD_WARPS warps; lane = proof, so every warp runs one straight-line task
+// for 32 proofs and the block synchronises between the four dependency phases.  Writes heads[p] and the proof's tables.
+#define RP_HEAD_WARPS 8
+__global__ void __launch_bounds__(32 * RP_HEAD_WARPS) k_rp_head(const uint8_t *__restrict__ proofs, rp_geom g, const uint8_t *__restrict__ raw, uint32_t count,
+                                                               rp_head *__restrict__ heads, sc *__restrict__ tabs, const sc *__restrict__ pow2,
+                                                               rp_work *__restrict__ work, uint32_t *__restrict__ status) {
+    const uint32_t lane = threadIdx.x & 31, wq = threadIdx.x >> 5, p = blockIdx.x * 32 + lane;
+    const bool in = p < count;
+    const uint32_t pc = in ? p : count - 1;
+    const uint32_t k = g.k, n = g.n, m = g.m, kl = rp_kl(k), kh = k - kl, TL = 1u << kl, TH = 1u << kh;
+    bool ok = in && status[pc] == BP_PROOF_OK;
+    const uint8_t *proof = proofs + (size_t)pc * g.proof_len, *rw = raw + (size_t)pc * (RP_RAW_U + k) * 64;
+    rp_work &W = work[pc]; rp_head &h = heads[pc];
+    rp_tabs T = rp_tab_ptrs(tabs + (size_t)pc * rp_tab_size(k, m), k);
+    // ---- phase A: reduce the challenges mod l, proof scalars to Montgomery form
+    if (ok) for (uint32_t it = wq; it < RP_RAW_U + k + 5; it += RP_HEAD_WARPS) {
+        if (it < RP_RAW_U + k) { sc v = rp_wide(rw + 64 * it); if (it < RP_RAW_U) W.ch[it] = v; else W.u[it - RP_RAW_U] = v; }
+        else {
+            uint32_t j = it - RP_RAW_U - k;                 // a, b, t_x, t_x_blinding, e_blinding
+            const uint8_t *src = j < 2 ? proof + 224 + 64 * k + 32 * j : proof + 128 + 32 * (j - 2);
+            W.pf[j] = sc_to_mont(sc_load(src));
+        }
+    }
+    __syncthreads();
+    if (ok) {       // zero challenges: see rp_transcript; every warp takes the same decision
+        bool bad = sc_is_zero(W.ch[RP_RAW_Y]);
+        for (uint32_t j = 0; j < k; j++) bad = bad || sc_is_zero(W.u[j]);
+        if (bad) { ok = false; if (wq == 0) status[p] = BP_PROOF_VERIFICATION_ERROR; }
+    }
+    if (wq == 0 && in) h.status = ok ? (uint32_t)BP_PROOF_OK : (status[p] == BP_PROOF_OK ? (uint32_t)BP_PROOF_VERIFICATION_ERROR : status[p]);
+    sc y, z, rho;
+    if (ok) { y = W.ch[RP_RAW_Y]; z = W.ch[RP_RAW_Z]; rho = W.ch[RP_RAW_RHO]; if (sc_is_zero(rho)) rho = sc_mont_one(); }
+    // ---- phase B: the serial chains, one per warp
+    if (ok) switch (wq) {
+    case 0: { sc pre = sc_mont_one(); h.pre[0] = pre; for (uint32_t j = 0; j < k; j++) { sc us = sc_mm(W.u[j], W.u[j]); h.u_sq[j] = us; pre = sc_mm(pre, us); h.pre[j + 1] = pre; } } break;
+    case 1: { sc suf = sc_mont_one(); h.suf[k] = suf; for (int j = (int)k - 1; j >= 0; j--) { suf = sc_mm(suf, sc_mm(W.u[j], W.u[j])); h.suf[j] = suf; } } break;
+    case 2: { sc U = sc_mont_one(); for (uint32_t j = 0; j < k; j++) U = sc_mm(U, W.u[j]);
+              sc rhoU = sc_mm(rho, U); W.U = U; W.rhoU = rhoU; h.hB = sc_mm(W.pf[1], rhoU); W.hA = sc_mm(sc_mm(rhoU, U), sc_mm(z, z)); } break;
+    case 3: { sc yp = y, Y = y; W.ypow2[0] = yp; for (uint32_t j = 1; j < k; j++) { yp = sc_mm(yp, yp); W.ypow2[j] = yp; Y = sc_mm(Y, yp); }
+              if (k == 0) Y = sc_mont_one();
+              W.Y = Y; h.rhoY = sc_mm(rho, Y); } break;
+    case 4: { sc sum_y = rp_sum_of_powers_pow2(y, (uint64_t)n * m); W.t1 = sc_mm(sc_sub(z, sc_mm(z, z)), sum_y); } break;
+    case 5: { sc zz = sc_mm(z, z); h.z = z; h.zz = zz;
+              sc sum_z = rp_sum_of_powers_pow2(z, m), sum_2 = sc_mont_from_u64(n == 64 ? ~0ULL : ((1ULL << n) - 1));
+              W.d2 = sc_mm(sc_mm(sc_mm(zz, z), sum_2), sum_z); } break;
+    case 6: { const sc &a = W.pf[0], &b = W.pf[1], &t_x = W.pf[2], &w = W.ch[RP_RAW_W], &c = W.ch[RP_RAW_C];
+              W.e1 = sc_sub(sc_mm(w, sc_sub(t_x, sc_mm(a, b))), sc_mm(c, t_x));
+              W.bl = sc_neg(sc_add(W.pf[4], sc_mm(c, W.pf[3]))); } break;
+    default: break;
+    }
+    __syncthreads();
+    // ---- phase C: the four subset-product tables, the lambda chain, gA
+    if (ok) switch (wq) {
+    case 0: RP_BUILD_TABLE(T.s_lo, kl, h.u_sq[(k - 1) - b_]); break;
+    case 1: RP_BUILD_TABLE(T.s_hi, kh, h.u_sq[(k - 1) - kl - b_]); break;
+    case 2: RP_BUILD_TABLE(T.y_lo, kl, W.ypow2[b_]); break;
+    case 3: RP_BUILD_TABLE(T.y_hi, kh, W.ypow2[kl + b_]); break;
+    case 4: { const sc &x = W.ch[RP_RAW_X], &c = W.ch[RP_RAW_C];
+              sc L = sc_mm(rho, sc_mm(h.pre[k], W.Y)); h.L = L; h.zL = sc_mm(z, L);
+              sc Lx = sc_mm(L, x), Lcx = sc_mm(Lx, c); h.Lx = Lx; h.Lcx = Lcx; h.Lcxx = sc_mm(Lcx, x); h.Lczz = sc_mm(sc_mm(L, c), sc_mm(z, z));
+              // basepoint scalar w (t_x - a b) + c (delta - t_x) = e1 + c delta,  delta = t1 - d2   (mod.rs:419, 587-593);  blinding scalar -e~ - c t~  (mod.rs:430)
+              sc bs = sc_add(W.e1, sc_mm(c, sc_sub(W.t1, W.d2)));
+              h.basepoint_scalar = sc_mm(L, bs); h.blinding_scalar = sc_mm(L, W.bl); } break;
+    case 5: h.gA = sc_mm(sc_mm(W.pf[0], W.rhoU), W.Y); break;
+    default: break;
+    }
+    __syncthreads();
+    // ---- phase D: the mixed tables, entries dealt round-robin to four warps each
+    if (ok) {
+        if (wq < 4) {
+            for (uint32_t v = wq; v < TL; v += 4) {
+                sc F = sc_mm(pow2[v % n], rp_pow_small(z, v / n));
+                T.P_lo[v] = sc_mm(T.y_lo[v ^ (TL - 1)], F);
+                T.Q_lo[v] = sc_mm(T.y_lo[v ^ (TL - 1)], T.s_lo[v ^ (TL - 1)]);
+            }
+        } else {
+            for (uint32_t v = wq - 4; v < TH; v += 4) {
+                uint64_t idx = (uint64_t)v << kl;
+                sc F = sc_mm(pow2[idx % n], rp_pow_small(z, (uint32_t)(idx / n)));
+                sc yc = T.y_hi[v ^ (TH - 1)];
+                T.A_hi[v] = sc_mm(h.gA, T.s_hi[v]);
+                T.P_hi[v] = sc_mm(sc_mm(W.hA, yc), F);
+                T.Q_hi[v] = sc_mm(sc_mm(h.hB, yc), T.s_hi[v ^ (TH - 1)]);
+            }
+        }
+    }
 }
 // K5: verification scalars, fully data-parallel: one thread per (proof, term) with term in
 // [0, N) -> (g_i, h_i) and [N, N + D) -> the per-proof scalars.

@@ -42,42 +42,60 @@ BP_HD bool bp_is_zero32(const uint8_t *p) { uint8_t z = 0; for (int i = 0; i < 3
 BP_HD sc rp_wide(const uint8_t buf[64]) { sc lo = sc_load(buf), hi = sc_load(buf + 32); return sc_add(sc_mm(lo, sc{SC_RR_LIMBS}), sc_mm(hi, sc{SC_RRR_LIMBS})); }
 BP_HD sc rp_challenge(merlin_t &t, const char *label) { uint8_t buf[64]; merlin_challenge(t, label, buf, 64); return rp_wide(buf); }
 
-// Transcript replay of one proof.  proof = 32*(9+2k) bytes, V = m*32 bytes, tstate = the serialized
-// transcript the caller passed in, weights = 128 bytes of per-proof randomness (c, rho),
-// state200 = 200 bytes of 4-byte-aligned scratch for the STROBE state.
-BP_HDN void rp_transcript(rp_challenges &ch, const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t n, uint32_t m,
-                         const uint8_t *tstate, const uint8_t *weights, uint8_t *state200) {
-    ch.status = BP_PROOF_OK;
+// Transcript replay of one proof: pure hashing.  proof = 32*(9+2k) bytes, V = m*32 bytes, tstate = the serialized
+// transcript the caller passed in, state200 = 200 bytes of 4-byte-aligned scratch for the STROBE state.
+// Output: the 64-byte challenge outputs in the order y, z, x, w, (c, rho: filled by the caller from the weights), u_0..u_{k-1}
+// -> raw[RP_RAW_U + j]; nothing the verifier hashes depends on a challenge, so the reduction mod l is left to the caller.
+#define RP_RAW_Y 0
+#define RP_RAW_Z 1
+#define RP_RAW_X 2
+#define RP_RAW_W 3
+#define RP_RAW_C 4
+#define RP_RAW_RHO 5
+#define RP_RAW_U 6
+BP_HD void rp_raw_challenge(merlin_t &t, const char *label, uint8_t *out64) { merlin_challenge(t, label, out64, 64); }
+BP_HDN uint32_t rp_transcript_raw(uint8_t (*raw)[64], const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t n, uint32_t m,
+                                  const uint8_t *tstate, uint8_t *state200) {
     const uint8_t *A = proof, *S = proof + 32, *T1 = proof + 64, *T2 = proof + 96;
     const uint8_t *LR = proof + 224, *ab = proof + 224 + 64 * k;
     // RangeProof::from_bytes / InnerProductProof::from_bytes canonicity (mod.rs:519-524, inner_product_proof.rs:399-404)
-    if (sc_geq_l(sc_load(proof + 128)) || sc_geq_l(sc_load(proof + 160)) || sc_geq_l(sc_load(proof + 192)) || sc_geq_l(sc_load(ab)) || sc_geq_l(sc_load(ab + 32))) {
-        ch.status = BP_PROOF_FORMAT_ERROR; return;
-    }
+    if (sc_geq_l(sc_load(proof + 128)) || sc_geq_l(sc_load(proof + 160)) || sc_geq_l(sc_load(proof + 192)) || sc_geq_l(sc_load(ab)) || sc_geq_l(sc_load(ab + 32)))
+        return BP_PROOF_FORMAT_ERROR;
     merlin_t t; t.st = state200; merlin_load(t, tstate);
     merlin_append(t, "dom-sep", (const uint8_t *)"rangeproof v1", 13);            // transcript.rs:44-48
     merlin_append_u64(t, "n", n); merlin_append_u64(t, "m", m);
     for (uint32_t j = 0; j < m; j++) merlin_append(t, "V", V + 32 * j, 32);         // mod.rs:370-374 (identity allowed)
     bool bad = bp_is_zero32(A) || bp_is_zero32(S);                                  // validate_and_append_point
     merlin_append(t, "A", A, 32); merlin_append(t, "S", S, 32);
-    ch.y = rp_challenge(t, "y"); ch.z = rp_challenge(t, "z");
+    rp_raw_challenge(t, "y", raw[RP_RAW_Y]); rp_raw_challenge(t, "z", raw[RP_RAW_Z]);
     bad = bad || bp_is_zero32(T1) || bp_is_zero32(T2);
     merlin_append(t, "T_1", T1, 32); merlin_append(t, "T_2", T2, 32);
-    ch.x = rp_challenge(t, "x");
+    rp_raw_challenge(t, "x", raw[RP_RAW_X]);
     merlin_append(t, "t_x", proof + 128, 32); merlin_append(t, "t_x_blinding", proof + 160, 32); merlin_append(t, "e_blinding", proof + 192, 32);
-    ch.w = rp_challenge(t, "w");
+    rp_raw_challenge(t, "w", raw[RP_RAW_W]);
     merlin_append(t, "dom-sep", (const uint8_t *)"ipp v1", 6);                      // transcript.rs:50-53
     merlin_append_u64(t, "n", (uint64_t)n * m);
     for (uint32_t j = 0; j < k; j++) {                                              // inner_product_proof.rs:218-222
         bad = bad || bp_is_zero32(LR + 64 * j) || bp_is_zero32(LR + 64 * j + 32);
         merlin_append(t, "L", LR + 64 * j, 32); merlin_append(t, "R", LR + 64 * j + 32, 32);
-        ch.u[j] = rp_challenge(t, "u");
+        rp_raw_challenge(t, "u", raw[RP_RAW_U + j]);
     }
+    return bad ? BP_PROOF_VERIFICATION_ERROR : BP_PROOF_OK;
+}
+// Sequential form (host emulation, reference for the cooperative device head): replay + reduction of the challenges.
+// weights = 128 bytes of per-proof randomness (c, rho).
+BP_HDN void rp_transcript(rp_challenges &ch, const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t n, uint32_t m,
+                         const uint8_t *tstate, const uint8_t *weights, uint8_t *state200) {
+    uint8_t raw[RP_RAW_U + BP_MAX_LG_N][64];
+    ch.status = rp_transcript_raw(raw, proof, k, V, n, m, tstate, state200);
+    if (ch.status != BP_PROOF_OK) return;
+    ch.y = rp_wide(raw[RP_RAW_Y]); ch.z = rp_wide(raw[RP_RAW_Z]); ch.x = rp_wide(raw[RP_RAW_X]); ch.w = rp_wide(raw[RP_RAW_W]);
+    for (uint32_t j = 0; j < k; j++) ch.u[j] = rp_wide(raw[RP_RAW_U + j]);
     // The device multiplies the proof's check by lambda = (prod u_j)^2 y^(N-1) (see the header).  A zero challenge would make
     // lambda vanish and the proof drop out of the combination, so it is rejected outright; the reference cannot verify such a
     // transcript either (u_j = 0 has no inverse), and an honest or dishonest prover hits it with probability ~2^-252 per hash.
+    bool bad = sc_is_zero(ch.y);
     for (uint32_t j = 0; j < k; j++) bad = bad || sc_is_zero(ch.u[j]);
-    bad = bad || sc_is_zero(ch.y);
     if (bad) { ch.status = BP_PROOF_VERIFICATION_ERROR; return; }
     ch.c = rp_wide(weights); ch.rho = rp_wide(weights + 64);
     if (sc_is_zero(ch.rho)) ch.rho = sc_mont_one();                  // a zero weight (probability 2^-252) would skip the proof
@@ -88,6 +106,14 @@ struct rp_head {                // Montgomery form; "L" = Lambda = rho * lambda
     sc z, zz, L, zL, Lx, Lcx, Lcxx, Lczz, gA, hB, rhoY;
     sc u_sq[BP_MAX_LG_N], pre[BP_MAX_LG_N + 1], suf[BP_MAX_LG_N + 1];
     sc basepoint_scalar, blinding_scalar;
+};
+
+// Scratch of the cooperative head kernel (k_rp_head), one per proof, Montgomery form
+struct rp_work {
+    sc ch[6];                       // y, z, x, w, c, rho  (RP_RAW_* order)
+    sc pf[5];                       // a, b, t_x, t_x_blinding, e_blinding
+    sc u[BP_MAX_LG_N], ypow2[BP_MAX_LG_N];
+    sc U, Y, rhoU, hA, t1, d2, e1, bl;
 };
 
 // Per-proof product tables (global memory, rp_tab_size() scalars per proof) that turn the tail into three products

@@ -157,6 +157,9 @@ int bp_prof_enable(bp_ctx *ctx, int on);
 int bp_prof_kernel_count(void);
 const char *bp_prof_kernel_name(int kernel_id);
 int bp_prof_report(bp_ctx *ctx, double *ms, uint64_t *counts);
+/* Per-launch records (kernel id, start, end in ms relative to the first record of `ref`, another context of the same device)
+ * accumulated since profiling was enabled; does not clear them.  Diagnostic for multi-stream overlap (benchmarks/timeline.py). */
+int bp_prof_timeline(bp_ctx *ctx, bp_ctx *ref, int *kernel_ids, double *start_ms, double *end_ms, size_t cap, size_t *n_out);
 
 /* ---- host helpers -------------------------------------------------------------------------- */
 /* merlin::Transcript for callers without the Rust crate (same framing as transcript.rs:43-94 expects):

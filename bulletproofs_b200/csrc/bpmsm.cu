@@ -126,7 +126,7 @@ int msm_core(bp_ctx *ctx, const MsmArgs &a, ge_ext *d_results) {
     LAUNCH(ctx, KID_MSM_SCATTER, k_msm_scatter<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>()));
     LAUNCH(ctx, KID_MSM_ACCUMULATE, k_msm_accumulate<<<blocks_for(n_buckets, 128), 128, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(), a.d_offsets, ctx->order.as<uint32_t>(), W, nb,
                                                                 n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>(), heavy_min));
-    LAUNCH(ctx, KID_MSM_ACC_HEAVY, k_msm_accumulate_heavy<<<(unsigned)std::min<size_t>(heavy_cap, 2 * 148), MSM_HEAVY_THREADS, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(),
+    LAUNCH(ctx, KID_MSM_ACC_HEAVY, k_msm_accumulate_heavy<<<(unsigned)std::min<size_t>(heavy_cap, 148), MSM_HEAVY_THREADS, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(),
                                                                 a.d_offsets, heavy_n, heavy, W, nb, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>()));
     unsigned rthreads = nb >= 64 ? 64 : 32;      // two warps per segment: fewer scan/tree additions per useful bucket addition
     LAUNCH(ctx, KID_MSM_REDUCE, k_msm_reduce<<<(unsigned)segs, rthreads, 0, s>>>(ctx->buckets.as<ge_ext>(), nb, ctx->wsums.as<ge_ext>()));
@@ -162,7 +162,6 @@ __global__ void k_rp_point_idx(rp_geom g, uint32_t gens_cap, uint32_t gens_parti
     else v = BP_POINT_DYNAMIC | (per_proof_rows ? (p * g.D + (t - g.S)) : (uint32_t)(i - g.S));
     out[i] = v;
 }
-__global__ void k_noop() {}
 __global__ void k_fill_offsets(uint32_t n, uint32_t stride, uint32_t *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n) out[i] = i * stride;
@@ -416,8 +415,6 @@ static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t 
     if (rc) return rc;
     LAUNCH(c, KID_SMALL, k_is_identity<<<1, 32, 0, s>>>(c->results.as<ge_ext>(), 1, c->flags.as<uint32_t>()));
     LAUNCH(c, KID_SMALL, k_rp_verdict<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>(), c->flags.as<uint32_t>(), 0, count, d_verdict, d_batch_ok));
-    { static int dummy = getenv("BP_DUMMY_LAUNCHES") ? atoi(getenv("BP_DUMMY_LAUNCHES")) : 0;      // EXPERIMENT
-      for (int i = 0; i < dummy; i++) k_noop<<<1, 32, 0, s>>>(); }
     return BP_OK;
 }
 

@@ -272,7 +272,14 @@ BP_HD fe fe_reduce_wide(const uint32_t t[16]) {
     return r;
 }
 
-BP_HD fe fe_mul(const fe &a, const fe &b) { uint32_t t[16]; fe_mul_wide(t, a, b); return fe_reduce_wide(t); }
+// -DBP_NOINLINE_MUL: out-of-line multiplier (5x faster compile, 3x smaller kernels, ~7 % slower verification on B200:
+// the field elements then travel through local memory) -- for debug builds only
+#ifdef BP_NOINLINE_MUL
+#define BP_FEMUL BP_HDN
+#else
+#define BP_FEMUL BP_HD
+#endif
+BP_FEMUL fe fe_mul(const fe &a, const fe &b) { uint32_t t[16]; fe_mul_wide(t, a, b); return fe_reduce_wide(t); }
 // 16-limb square t = a*a: 28 off-diagonal products (each used once, then doubled) + 8 diagonal ones
 BP_HD void fe_sq_wide(uint32_t t[16], const fe &A) {
 #ifdef __CUDA_ARCH__
@@ -386,7 +393,7 @@ BP_HD void fe_sq_wide(uint32_t t[16], const fe &A) {
     fe_mul_wide(t, A, A);
 #endif
 }
-BP_HD fe fe_sq(const fe &a) { uint32_t t[16]; fe_sq_wide(t, a); return fe_reduce_wide(t); }
+BP_FEMUL fe fe_sq(const fe &a) { uint32_t t[16]; fe_sq_wide(t, a); return fe_reduce_wide(t); }
 BP_HD fe fe_sqn(fe a, int n) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1

@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(128, 5) k_msm_accumulate(const uint32_t *__res
 }
 // pass 4b: heavy buckets, one block per bucket (grid-stride over the list k_msm_order built): threads take strided
 // entries, then a shuffle tree + one shared-memory round add the partial sums
-#define MSM_HEAVY_THREADS 512
+#define MSM_HEAVY_THREADS 256      // 256 x 118 registers: two blocks fit beside other kernels' blocks on an SM
 __global__ void __launch_bounds__(MSM_HEAVY_THREADS) k_msm_accumulate_heavy(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
                                                         const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ heavy_n, const uint32_t *__restrict__ heavy, int W, uint32_t nb,
                                                         const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,

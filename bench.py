@@ -51,8 +51,10 @@ def effective_cores():
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture
 # profiles/r1_final_ncu_full.md; the scratch arrays (sorted ids, buckets, contrib) make it larger than the algorithmic bytes
-NCU_TRAFFIC_BYTES = {"k_msm_accumulate": 3.72e6, "k_msm_reduce": 3.37e6, "k_msm_combine": 0.025e6, "k_rp_transcript": 1.05e6,
+NCU_TRAFFIC_BYTES = {"k_msm_accumulate": 3.72e6, "k_msm_reduce": 3.37e6, "k_msm_combine": 0.025e6, "k_rp_transcript": 0.77e6, "k_rp_head": 1.29e6,
                      "k_rp_scalars": 2.93e6, "k_rp_decompress": 0.83e6, "k_rp_static_reduce": 4.27e6}
+# sm__pipe_fmaheavy_cycles_active x elapsed cycles summed over the kernels of one config-2 batch, per SM, same capture
+NCU_FMAHEAVY_BUSY_CYCLES_PER_SM = 142800
 
 
 def make_workload(count, rank):
@@ -324,6 +326,10 @@ def main():
     INT_PEAK = 9.25e12
     int_pipe = {"unit": "wide multiply-adds/s (IMAD.WIDE.U32, thread level)", "per_step": wide, "achieved": wide * (value / world / BATCH), "peak": INT_PEAK,
                 "frac": wide * (value / world / BATCH) / INT_PEAK, "peak_source": "measured, benchmarks/imad_microbench.cu (profiles/r1_imad_peak.md)"}
+    if (M_PARTIES, BATCH) == (1, 1024) and clocks.get("sm_mhz"):
+        # the same fraction from the hardware counter of the committed ncu capture: busy cycles of the FMA-heavy pipe per batch / cycles per batch
+        int_pipe["ncu_fmaheavy"] = {"busy_cycles_per_sm_per_step": NCU_FMAHEAVY_BUSY_CYCLES_PER_SM,
+                                    "frac": NCU_FMAHEAVY_BUSY_CYCLES_PER_SM / (ms_dev / args.steps * 1e-3 * clocks["sm_mhz"] * 1e6), "source": "profiles/r1_final_ncu_full.md"}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

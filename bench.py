@@ -155,7 +155,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=24)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--streams", type=int, default=24)
-    ap.add_argument("--threads", type=int, default=1, help="host threads issuing steps (each drives streams/threads contexts)")
+    ap.add_argument("--threads", type=int, default=0, help="host threads issuing steps (each drives streams/threads contexts); 0 = min(3, host cores per rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--m", type=int, default=M_PARTIES, help="parties per proof (BASELINE config 3: --m 16 --batch 256); the bench line is the default")
     ap.add_argument("--batch", type=int, default=BATCH, help="proofs per verified batch")
@@ -226,7 +226,8 @@ def main():
             torch.cuda.synchronize()
 
     from concurrent.futures import ThreadPoolExecutor
-    NT = max(1, min(args.threads, S))
+    NT = args.threads if args.threads > 0 else min(3, max(1, effective_cores() // world))     # 3 issuing threads: e2e +5 % over one (profiles/r1_timeline.md)
+    NT = max(1, min(NT, S))
     pool = ThreadPoolExecutor(NT) if NT > 1 else None
 
     def run_steps(step_fn, first, n):

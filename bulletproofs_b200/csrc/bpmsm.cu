@@ -44,7 +44,7 @@ struct VerifyState {          // what bp_rangeproof_verify_begin leaves for _fin
 }  // namespace
 
 struct bp_ctx {
-    int device = 0; cudaStream_t stream = nullptr; bool own_stream = false;
+    int device = 0, sm_count = 148; cudaStream_t stream = nullptr; bool own_stream = false;
     std::string err; uint64_t launches = 0;
     bool prof_on = false; std::vector<ProfRec> prof;          // per-kernel CUDA-event timing (bp_prof_*)
     // MSM scratch
@@ -124,8 +124,13 @@ int msm_core(bp_ctx *ctx, const MsmArgs &a, ge_ext *d_results) {
     LAUNCH(ctx, KID_MSM_SCAN, k_msm_scan<<<(unsigned)segs, 256, 0, s>>>(ctx->counts.as<uint32_t>(), nb, ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), size_hist));
     LAUNCH(ctx, KID_MSM_SCAN, k_msm_order<<<blocks_for(n_buckets, 256), 256, 0, s>>>(ctx->counts.as<uint32_t>(), n_buckets, size_hist, bin_cursor, ctx->order.as<uint32_t>(), heavy_min, heavy_n, heavy));
     LAUNCH(ctx, KID_MSM_SCATTER, k_msm_scatter<<<blocks_for(a.T, 256), 256, 0, s>>>(a.d_scalars, a.d_offsets, a.n_msm, a.T, c, W, ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>()));
-    LAUNCH(ctx, KID_MSM_ACCUMULATE, k_msm_accumulate<<<blocks_for(n_buckets, 128), 128, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(), a.d_offsets, ctx->order.as<uint32_t>(), W, nb,
-                                                                n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>(), heavy_min));
+    // two lanes per bucket once buckets hold >= 8 terms on average: half the serial chain per thread and twice the warps in flight for
+    // one extra addition per bucket (config 2: 108 -> 71 us alone, same throughput with 24 batches in flight; profiles/r1_timeline.md)
+    const int acc_split = avg / nb >= 8 ? 2 : 1;
+#define ACC_LAUNCH(SP) LAUNCH(ctx, KID_MSM_ACCUMULATE, k_msm_accumulate<SP><<<blocks_for(n_buckets * SP, 128), 128, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(), \
+        a.d_offsets, ctx->order.as<uint32_t>(), W, nb, n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>(), heavy_min))
+    if (acc_split == 2) ACC_LAUNCH(2); else ACC_LAUNCH(1);
+#undef ACC_LAUNCH
     LAUNCH(ctx, KID_MSM_ACC_HEAVY, k_msm_accumulate_heavy<<<(unsigned)std::min<size_t>(heavy_cap, 148), MSM_HEAVY_THREADS, 0, s>>>(ctx->starts.as<uint32_t>(), ctx->cursor.as<uint32_t>(), ctx->sorted.as<uint32_t>(),
                                                                 a.d_offsets, heavy_n, heavy, W, nb, a.d_point_idx, a.d_static, a.d_dynamic, ctx->buckets.as<ge_ext>()));
     unsigned rthreads = nb >= 64 ? 64 : 32;      // two warps per segment: fewer scan/tree additions per useful bucket addition
@@ -183,7 +188,7 @@ int bp_ctx_create(int device, void *stream, bp_ctx **out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return BP_ERR_CUDA;   // sm_100a only
     bp_ctx *c = new bp_ctx();
-    c->device = device;
+    c->device = device; c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else { if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return BP_ERR_CUDA; } c->own_stream = true; }
     if (cudaMallocHost((void **)&c->h_flag, 64) != cudaSuccess) { delete c; return BP_ERR_CUDA; }

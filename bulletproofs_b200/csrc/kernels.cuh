@@ -247,21 +247,27 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *__restrict__
         sorted[msm_slice_base(o0, len, (uint32_t)w, W) + pos] = t | (d < 0 ? 0x80000000u : 0u);
     }
 }
-// pass 4: bucket accumulation, one thread per bucket: sum of +-points listed in its slice (mixed additions)
+// pass 4: bucket accumulation, SPLIT adjacent lanes per bucket: each sums every SPLIT-th +-point of the bucket's slice (mixed
+// additions), a shuffle tree adds the partial sums.  SPLIT > 1 trades (SPLIT-1) full additions per bucket for SPLIT x more warps
+// in flight and a SPLIT x shorter serial chain per thread.
+template <int SPLIT>
 __global__ void __launch_bounds__(128, 5) k_msm_accumulate(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
                                                         const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, int W, uint32_t nb, size_t n_buckets,
                                                         const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,
                                                         ge_ext *__restrict__ buckets, uint32_t heavy_min) {
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= n_buckets) return;
-    size_t gb = order[tid];
+    size_t b = tid / SPLIT; uint32_t sub = (uint32_t)(tid % SPLIT);
+    bool live = b < n_buckets;
+    if (SPLIT == 1 && !live) return;
+    size_t gb = live ? order[b] : 0;
     size_t seg = gb / nb; uint32_t msm = (uint32_t)(seg / W), w = (uint32_t)(seg % W);
     uint32_t o0 = __ldg(offsets + msm), len = __ldg(offsets + msm + 1) - o0;
     const uint32_t *slice = sorted + msm_slice_base(o0, len, w, W);
     uint32_t lo = starts[gb], hi = ends[gb];
-    if (hi - lo >= heavy_min) return;           // k_msm_accumulate_heavy owns this bucket
+    if (hi - lo >= heavy_min) live = false;     // k_msm_accumulate_heavy owns this bucket
+    if (!live) { if (SPLIT == 1) return; lo = hi = 0; }
     ge_ext acc = ge_identity();
-    for (uint32_t e = lo; e < hi; e++) {
+    for (uint32_t e = lo + sub; e < hi; e += SPLIT) {
         uint32_t v = __ldg(slice + e), t = v & 0x7fffffffu;
         uint32_t pi = point_idx ? __ldg(point_idx + t) : (t | BP_POINT_DYNAMIC);
         const ge_niels *src = (pi & BP_POINT_DYNAMIC) ? pts_dynamic + (pi & 0x7fffffffu) : pts_static + pi;
@@ -269,7 +275,11 @@ __global__ void __launch_bounds__(128, 5) k_msm_accumulate(const uint32_t *__res
         if (v & 0x80000000u) q = ge_niels_neg(q);
         acc = ge_madd(acc, q);
     }
-    st_ext(buckets + gb, acc);
+    if (SPLIT > 1) {
+#pragma unroll 1
+        for (int d = SPLIT / 2; d >= 1; d >>= 1) { ge_ext o = shfl_down_ext(acc, d); acc = ge_add(acc, o); }
+    }
+    if (live && sub == 0) st_ext(buckets + gb, acc);
 }
 // pass 4b: heavy buckets, one block per bucket (grid-stride over the list k_msm_order built): threads take strided
 // entries, then a shuffle tree + one shared-memory round add the partial sums

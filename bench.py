@@ -51,10 +51,10 @@ def effective_cores():
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed `ncu --set full` capture
 # profiles/r1_final_ncu_full.md; the scratch arrays (sorted ids, buckets, contrib) make it larger than the algorithmic bytes
-NCU_TRAFFIC_BYTES = {"k_msm_accumulate": 3.72e6, "k_msm_reduce": 3.37e6, "k_msm_combine": 0.025e6, "k_rp_transcript": 0.77e6, "k_rp_head": 1.29e6,
+NCU_TRAFFIC_BYTES = {"k_msm_accumulate": 3.91e6, "k_msm_reduce": 3.37e6, "k_msm_combine": 0.025e6, "k_rp_transcript": 0.77e6, "k_rp_head": 1.29e6,
                      "k_rp_scalars": 2.93e6, "k_rp_decompress": 0.83e6, "k_rp_static_reduce": 4.27e6}
 # sm__pipe_fmaheavy_cycles_active x elapsed cycles summed over the kernels of one config-2 batch, per SM, same capture
-NCU_FMAHEAVY_BUSY_CYCLES_PER_SM = 142800
+NCU_FMAHEAVY_BUSY_CYCLES_PER_SM = 151400
 
 
 def make_workload(count, rank):

@@ -110,6 +110,14 @@ def host_lib():
         H.bph_r1cs_prove.argtypes = [_vp, _vp, _sz, _sz, _u8p, _int, _u8p, _u8p, _sz, _c.c_uint64, _c.c_uint64, _u8p, _u8p, _c.POINTER(_sz), _u8p]
         H.bph_r1cs_verify.restype = _int
         H.bph_r1cs_verify.argtypes = [_vp, _vp, _sz, _sz, _u8p, _int, _u8p, _sz, _c.c_uint64, _u8p, _sz, _u8p]
+        u64 = _c.c_uint64
+        for name, args in (("bph_mpc_party_bit_commitment", [_vp, _vp, _sz, _sz, u64, _u8p, _sz, _sz, _u8p, _u8p]),
+                           ("bph_mpc_party_poly_commitment", [_vp, _vp, _sz, _sz, u64, _sz, _sz, _u8p, _u8p, _u8p, _u8p]),
+                           ("bph_mpc_party_proof_share", [_vp, _vp, _sz, _sz, u64, _u8p, _sz, _sz, _u8p, _u8p, _u8p, _u8p, _u8p]),
+                           ("bph_mpc_audit_share", [_vp, _vp, _sz, _sz, _sz, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _u8p]),
+                           ("bph_mpc_dealer_run", [_vp, _vp, _sz, _sz, _u8p, _sz, _sz, _u8p, _u8p, _u8p, _int, _u8p, _u8p, _u8p])):
+            getattr(H, name).restype = _int
+            getattr(H, name).argtypes = args
         _hlib = H
     return _hlib
 
@@ -397,3 +405,53 @@ def verify_batch(ctx: Context, gens: Gens, transcript: Transcript, proofs: bytes
     verdicts = ctypes.create_string_buffer(count)
     ctx._check(lib().bp_rangeproof_verify_batch(ctx._h, gens._h, transcript.to_bytes(), proofs, proof_len, commitments, n, m, count, seed, verdicts))
     return list(verdicts.raw)
+
+
+# ---- aggregated range-proof MPC (bulletproofs_b200/host/mpc.{hpp,cpp}: Party / Dealer typestates of src/range_proof/{party,dealer,messages}.rs).
+# Stateless harness form: a party is (v, v_blinding, n, j, ChaCha seed); wire layouts BitCommitment = V_j|A_j|S_j (96 B),
+# PolyCommitment = T_1_j|T_2_j (64 B), ProofShare = t_x|t_x_blinding|e_blinding|l_vec|r_vec (32*(3+2n) B).  Status codes: MPC_* below.
+MPC_OK, MPC_INVALID_BITSIZE, MPC_INVALID_GENERATORS_LENGTH, MPC_INVALID_AGGREGATION, MPC_MALICIOUS_DEALER, MPC_MALFORMED_PROOF_SHARES = 0, 3, 4, 5, 8, 10
+
+
+def _mpc_rc(ctx, rc):
+    if rc < 0:
+        raise BpError(rc, lib().bp_last_error(ctx._h).decode())
+    return rc
+
+
+def mpc_party_bit_commitment(ctx, gens, v: int, v_blinding: bytes, n: int, j: int, seed: bytes):
+    """Party::new + assign_position_with_rng(j, ChaChaRng::from_seed(seed)) -> (status, BitCommitment bytes)."""
+    out = ctypes.create_string_buffer(96)
+    rc = host_lib().bph_mpc_party_bit_commitment(ctx._h, gens._h, gens.gens_capacity, gens.party_capacity, v, v_blinding, n, j, seed, out)
+    return _mpc_rc(ctx, rc), out.raw
+
+
+def mpc_party_poly_commitment(ctx, gens, v: int, n: int, j: int, seed: bytes, y: bytes, z: bytes):
+    """... + apply_challenge_with_rng(BitChallenge{y, z}) -> (status, PolyCommitment bytes)."""
+    out = ctypes.create_string_buffer(64)
+    rc = host_lib().bph_mpc_party_poly_commitment(ctx._h, gens._h, gens.gens_capacity, gens.party_capacity, v, n, j, seed, y, z, out)
+    return _mpc_rc(ctx, rc), out.raw
+
+
+def mpc_party_proof_share(ctx, gens, v: int, v_blinding: bytes, n: int, j: int, seed: bytes, y: bytes, z: bytes, x: bytes):
+    """... + apply_challenge(PolyChallenge{x}) -> (status, ProofShare bytes); x = 0 -> MPC_MALICIOUS_DEALER."""
+    out = ctypes.create_string_buffer(32 * (3 + 2 * n))
+    rc = host_lib().bph_mpc_party_proof_share(ctx._h, gens._h, gens.gens_capacity, gens.party_capacity, v, v_blinding, n, j, seed, y, z, x, out)
+    return _mpc_rc(ctx, rc), out.raw
+
+
+def mpc_audit_share(ctx, gens, n: int, j: int, bit_commitment: bytes, y: bytes, z: bytes, poly_commitment: bytes, x: bytes, share: bytes) -> int:
+    """ProofShare::audit_share (messages.rs:84-167): 0 = Ok, 1 = Err."""
+    rc = host_lib().bph_mpc_audit_share(ctx._h, gens._h, gens.gens_capacity, gens.party_capacity, n, j, bit_commitment, y, z, poly_commitment, x, share)
+    return _mpc_rc(ctx, rc)
+
+
+def mpc_dealer_run(ctx, gens, transcript: Transcript, n: int, m: int, bit_commitments: bytes, poly_commitments: bytes = None, shares: bytes = None, trusted: bool = False):
+    """Dealer::new -> receive_bit_commitments [-> receive_poly_commitments [-> receive_shares | receive_trusted_shares]] over the messages given.
+    Returns (status, proof bytes or None, bad share flags, (y, z, x)); the transcript is advanced like the reference's &mut Transcript."""
+    proof = ctypes.create_string_buffer(rangeproof_size(n, m)); bad = ctypes.create_string_buffer(max(m, 1)); ch = ctypes.create_string_buffer(96)
+    rc = host_lib().bph_mpc_dealer_run(ctx._h, gens._h, gens.gens_capacity, gens.party_capacity, transcript.state, n, m, bit_commitments, poly_commitments, shares,
+                                       int(trusted), proof, bad, ch)
+    _mpc_rc(ctx, rc)
+    done = rc == 0 and shares is not None
+    return rc, (proof.raw if done else None), list(bad.raw[:m]), (ch.raw[:32], ch.raw[32:64], ch.raw[64:96])

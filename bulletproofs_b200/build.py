@@ -42,7 +42,7 @@ def build_host(force=False):
     lib = os.path.join(ROOT, "bulletproofs_b200", "libbulletproofs_host.so")
     srcs = [os.path.join(hdir, f) for f in os.listdir(hdir)] + [os.path.join(CSRC, f) for f in ("sc.cuh", "merlin.cuh", "fe.cuh")] + [LIB]
     if force or not _newer(lib, srcs):
-        _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", lib, os.path.join(hdir, "bulletproofs.cpp"), os.path.join(hdir, "r1cs.cpp"),
+        _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", lib, os.path.join(hdir, "bulletproofs.cpp"), os.path.join(hdir, "r1cs.cpp"), os.path.join(hdir, "mpc.cpp"),
               "-L" + os.path.join(ROOT, "bulletproofs_b200"), "-lbpmsm", "-Wl,-rpath,$ORIGIN"])
     return lib
 
@@ -50,7 +50,7 @@ def build_host(force=False):
 def build_oracle(force=False):
     odir = os.path.join(ROOT, "oracle")
     lib = os.path.join(odir, "liboracle.so")
-    srcs = [os.path.join(odir, f) for f in ("bp_oracle.c", "fe51.h", "sc.h", "ge.h", "hashes.h", "r1cs.h")]
+    srcs = [os.path.join(odir, f) for f in ("bp_oracle.c", "fe51.h", "sc.h", "ge.h", "hashes.h", "r1cs.h", "mpc.h")]
     if force or not _newer(lib, srcs):
         _run(["make", "-B", "-C", odir, "liboracle.so"])
     return lib

@@ -275,7 +275,7 @@ ProofError LinearProof::from_bytes(const uint8_t *s, size_t len, LinearProof &ou
 }
 
 // ------------------------------------------------------------------ RangeProof
-static Scalar scalar_exp_vartime(const Scalar &x, uint64_t n) {      // util.rs:222-234
+Scalar scalar_exp_vartime(const Scalar &x, uint64_t n) {      // util.rs:222-234
     Scalar result = Scalar::one(), aux = x;
     while (n > 0) { if (n & 1) result = result * aux; n >>= 1; aux = aux * aux; }
     return result;

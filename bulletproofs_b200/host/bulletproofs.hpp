@@ -63,6 +63,7 @@ public:
     Scalar invert() const { return Scalar(sc_mont_invert(m_)); }     // 0 -> 0, like dalek
 };
 Scalar inner_product(const std::vector<Scalar> &a, const std::vector<Scalar> &b);     // inner_product_proof.rs:418-427
+Scalar scalar_exp_vartime(const Scalar &x, uint64_t n);                               // util.rs:222-234
 
 class Transcript {
     alignas(8) uint8_t st_[200]; merlin_t m_;

@@ -425,6 +425,42 @@ int orc_rangeproof_prove(void *gens, const uint8_t *transcript_state, const uint
     chacha_rng rng; chacha_seed(&rng, rng_seed);
     return rp_prove(gens, default_pc(), &t, values, blindings, m, n, &rng, proof_out, V_out);
 }
+/* ------------------------------------------------------------------ aggregated range-proof MPC messages (party.rs, dealer.rs, messages.rs) */
+#include "mpc.h"
+static int load_sc(sc *r, const uint8_t b[32]) { return sc_from_canonical(r, b); }
+int orc_mpc_party_bit_commitment(void *gens, uint64_t v, const uint8_t v_blinding[32], size_t n, size_t j, const uint8_t seed[32], uint8_t out[96]) {
+    sc vb; if (!load_sc(&vb, v_blinding)) return ORC_NONCANONICAL_SCALAR;
+    return mpc_party_bit_commitment(gens, default_pc(), v, &vb, n, j, seed, out);
+}
+int orc_mpc_party_poly_commitment(void *gens, uint64_t v, size_t n, size_t j, const uint8_t seed[32], const uint8_t y[32], const uint8_t z[32], uint8_t out[64]) {
+    sc ys, zs; if (!load_sc(&ys, y) || !load_sc(&zs, z)) return ORC_NONCANONICAL_SCALAR;
+    return mpc_party_poly_commitment(gens, default_pc(), v, n, j, seed, &ys, &zs, out);
+}
+int orc_mpc_party_proof_share(void *gens, uint64_t v, const uint8_t v_blinding[32], size_t n, size_t j, const uint8_t seed[32], const uint8_t y[32], const uint8_t z[32],
+                              const uint8_t x[32], uint8_t *out) {
+    sc vb, ys, zs, xs; if (!load_sc(&vb, v_blinding) || !load_sc(&ys, y) || !load_sc(&zs, z) || !load_sc(&xs, x)) return ORC_NONCANONICAL_SCALAR;
+    return mpc_party_proof_share(gens, v, &vb, n, j, seed, &ys, &zs, &xs, out);
+}
+int orc_mpc_dealer_bit_challenge(void *gens, uint8_t *tstate, size_t n, size_t m, const uint8_t *bitc, uint8_t y_out[32], uint8_t z_out[32]) {
+    merlin t; memcpy(&t, tstate, sizeof t); sc y, z; uint8_t A[32], S[32];
+    int rc = mpc_dealer_bit_challenge(gens, &t, n, m, bitc, &y, &z, A, S); if (rc) return rc;
+    sc_tobytes(y_out, &y); sc_tobytes(z_out, &z); memcpy(tstate, &t, sizeof t); return ORC_OK;
+}
+int orc_mpc_dealer_poly_challenge(uint8_t *tstate, size_t m, const uint8_t *polyc, uint8_t x_out[32]) {
+    merlin t; memcpy(&t, tstate, sizeof t); sc x; uint8_t T1[32], T2[32];
+    int rc = mpc_dealer_poly_challenge(&t, m, polyc, &x, T1, T2); if (rc) return rc;
+    sc_tobytes(x_out, &x); memcpy(tstate, &t, sizeof t); return ORC_OK;
+}
+int orc_mpc_dealer_run(void *gens, const uint8_t *initial_tstate, size_t n, size_t m, const uint8_t *bitc, const uint8_t *polyc, const uint8_t *shares, int trusted,
+                       const uint8_t verify_seed[32], uint8_t *proof_out, uint8_t *bad) {
+    merlin t; memcpy(&t, initial_tstate, sizeof t);
+    return mpc_dealer_run(gens, default_pc(), &t, n, m, bitc, polyc, shares, trusted, verify_seed, proof_out, bad);
+}
+int orc_mpc_audit_share(void *gens, size_t n, size_t j, const uint8_t bitc[96], const uint8_t y[32], const uint8_t z[32], const uint8_t polyc[64], const uint8_t x[32], const uint8_t *share) {
+    sc ys, zs, xs; if (!load_sc(&ys, y) || !load_sc(&zs, z) || !load_sc(&xs, x)) return ORC_NONCANONICAL_SCALAR;
+    return mpc_audit_share(gens, default_pc(), n, j, bitc, &ys, &zs, polyc, &xs, share);
+}
+
 size_t orc_rangeproof_size(size_t n, size_t m) { return 32 * (9 + 2 * (size_t)lg2(n * m)); }
 
 /* vartime_multiscalar_mul on compressed inputs; out = compressed result */

@@ -41,6 +41,14 @@ class Oracle:
         L.orc_linear_verify.argtypes = [_p, _p, _sz, _p, _p, _p, _p, _p, _sz]
         L.orc_r1cs_prove.argtypes = [_vp, _p, ctypes.c_int, _p, _p, _sz, ctypes.c_uint64, ctypes.c_uint64, _p, _p, ctypes.POINTER(_sz), _p]
         L.orc_r1cs_verify.argtypes = [_vp, _p, ctypes.c_int, _p, _sz, ctypes.c_uint64, _p, _sz, _p]
+        u64 = ctypes.c_uint64
+        L.orc_mpc_party_bit_commitment.argtypes = [_vp, u64, _p, _sz, _sz, _p, _p]
+        L.orc_mpc_party_poly_commitment.argtypes = [_vp, u64, _sz, _sz, _p, _p, _p, _p]
+        L.orc_mpc_party_proof_share.argtypes = [_vp, u64, _p, _sz, _sz, _p, _p, _p, _p, _p]
+        L.orc_mpc_dealer_bit_challenge.argtypes = [_vp, _p, _sz, _sz, _p, _p, _p]
+        L.orc_mpc_dealer_poly_challenge.argtypes = [_p, _sz, _p, _p]
+        L.orc_mpc_dealer_run.argtypes = [_vp, _p, _sz, _sz, _p, _p, _p, ctypes.c_int, _p, _p, _p]
+        L.orc_mpc_audit_share.argtypes = [_vp, _sz, _sz, _p, _p, _p, _p, _p, _p]
         L.orc_init()
         assert L.orc_selfcheck() == 0
         self.tsize = L.orc_transcript_size()
@@ -186,3 +194,34 @@ class Oracle:
     def ipp_verify(self, tstate, n, Gf, Hf, P, Q, G, H, proof):
         st = ctypes.create_string_buffer(tstate, 256)
         return self.L.orc_ipp_verify(st, n, Gf, Hf, P, Q, G, H, proof, len(proof))
+
+    # aggregated range-proof MPC messages (oracle/mpc.h); stateless: a party is (v, v_blinding, n, j, seed)
+    def mpc_bit_commitment(self, g, v, v_blinding, n, j, seed):
+        o = ctypes.create_string_buffer(96)
+        return self.L.orc_mpc_party_bit_commitment(g, v, v_blinding, n, j, seed, o), o.raw
+
+    def mpc_poly_commitment(self, g, v, n, j, seed, y, z):
+        o = ctypes.create_string_buffer(64)
+        return self.L.orc_mpc_party_poly_commitment(g, v, n, j, seed, y, z, o), o.raw
+
+    def mpc_proof_share(self, g, v, v_blinding, n, j, seed, y, z, x):
+        o = ctypes.create_string_buffer(32 * (3 + 2 * n))
+        return self.L.orc_mpc_party_proof_share(g, v, v_blinding, n, j, seed, y, z, x, o), o.raw
+
+    def mpc_bit_challenge(self, g, tstate, n, m, bitc):
+        st = ctypes.create_string_buffer(tstate, len(tstate)); y = ctypes.create_string_buffer(32); z = ctypes.create_string_buffer(32)
+        rc = self.L.orc_mpc_dealer_bit_challenge(g, st, n, m, bitc, y, z)
+        return rc, st.raw, y.raw, z.raw
+
+    def mpc_poly_challenge(self, tstate, m, polyc):
+        st = ctypes.create_string_buffer(tstate, len(tstate)); x = ctypes.create_string_buffer(32)
+        rc = self.L.orc_mpc_dealer_poly_challenge(st, m, polyc, x)
+        return rc, st.raw, x.raw
+
+    def mpc_dealer_run(self, g, initial_tstate, n, m, bitc, polyc, shares, trusted=False, verify_seed=bytes(32)):
+        proof = ctypes.create_string_buffer(self.rangeproof_size(n, m)); bad = ctypes.create_string_buffer(m)
+        rc = self.L.orc_mpc_dealer_run(g, initial_tstate, n, m, bitc, polyc, shares, int(trusted), verify_seed, proof, bad)
+        return rc, proof.raw, list(bad.raw)
+
+    def mpc_audit_share(self, g, n, j, bitc, y, z, polyc, x, share):
+        return self.L.orc_mpc_audit_share(g, n, j, bitc, y, z, polyc, x, share)

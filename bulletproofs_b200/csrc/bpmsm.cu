@@ -54,6 +54,10 @@ struct bp_ctx {
     DevBuf fb_scalars, fb_pidx, fb_offsets;
     uint32_t *h_verdict = nullptr; size_t h_verdict_cap = 0;       // pinned
     uint32_t *h_flag = nullptr;                                      // pinned, 4 words
+    // pinned staging ring for the per-call parameter block of the verifier: a slot is reused only after the upload queued from it has
+    // completed, so back-to-back bp_rangeproof_verify_batch_device calls on one context never see each other's parameters
+    static const int STAGE_SLOTS = 8;
+    uint8_t *h_stage = nullptr; cudaEvent_t stage_ev[STAGE_SLOTS] = {}; unsigned stage_next = 0;
     VerifyState vs;
     size_t pidx_key[5] = {0, 0, 0, 0, 0};                           // geometry the cached rp_pidx map was built for
 };
@@ -192,6 +196,8 @@ int bp_ctx_create(int device, void *stream, bp_ctx **out) {
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else { if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return BP_ERR_CUDA; } c->own_stream = true; }
     if (cudaMallocHost((void **)&c->h_flag, 64) != cudaSuccess) { delete c; return BP_ERR_CUDA; }
+    if (cudaMallocHost((void **)&c->h_stage, 512 * bp_ctx::STAGE_SLOTS) != cudaSuccess) { cudaFreeHost(c->h_flag); delete c; return BP_ERR_CUDA; }
+    for (int i = 0; i < bp_ctx::STAGE_SLOTS; i++) cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming);
     *out = c;
     return BP_OK;
 }
@@ -205,6 +211,8 @@ void bp_ctx_destroy(bp_ctx *c) {
     for (DevBuf *b : bufs) b->release();
     if (c->h_verdict) cudaFreeHost(c->h_verdict);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    for (int i = 0; i < bp_ctx::STAGE_SLOTS; i++) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -376,20 +384,22 @@ static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t 
     CK(c, c->rp_status.ensure((size_t)count * 4)); CK(c, c->niels.ensure((size_t)count * g.D * sizeof(ge_niels)));
     CK(c, c->rp_pidx.ensure((size_t)T * 4)); CK(c, c->rp_offsets.ensure(8)); CK(c, c->results.ensure(sizeof(ge_ext)));
     CK(c, c->flags.ensure(16)); CK(c, c->rp_batch_ok.ensure(4));
-    // small parameter uploads go through the pinned 64-byte scratch word? no: they are read before the call returns only when pageable,
-    // so stage them in the context's own pinned buffer
-    if (!c->h_verdict || c->h_verdict_cap < (size_t)count + 128) {
+    if (!c->h_verdict || c->h_verdict_cap < (size_t)count) {
         if (c->h_verdict) cudaFreeHost(c->h_verdict);
         c->h_verdict = nullptr; c->h_verdict_cap = 0;
-        CK(c, cudaMallocHost((void **)&c->h_verdict, ((size_t)count + 128) * 4));
-        c->h_verdict_cap = (size_t)count + 128;
+        CK(c, cudaMallocHost((void **)&c->h_verdict, (size_t)count * 4));
+        c->h_verdict_cap = (size_t)count;
     }
-    uint8_t *stage = reinterpret_cast<uint8_t *>(c->h_verdict + count);     // 512 pinned bytes behind the verdicts
+    // one 512-byte parameter block: transcript (0..202) | seed (256..287) | MSM offsets (320..327) | batch flag (336..339), staged in pinned
+    // memory of the context so that the asynchronous upload never reads caller memory after this function returns
+    unsigned slot = c->stage_next++ % bp_ctx::STAGE_SLOTS;
+    CK(c, cudaEventSynchronize(c->stage_ev[slot]));                          // the upload that last used this slot is done
+    uint8_t *stage = c->h_stage + 512 * slot;
     memcpy(stage, h_transcript, BP_TRANSCRIPT_BYTES); memcpy(stage + 256, seedbuf, 32);
     uint32_t offs[2] = {0, T}; memcpy(stage + 320, offs, 8);
     uint32_t one = 1; memcpy(stage + 336, &one, 4);
-    // one 512-byte parameter block: transcript (0..202) | seed (256..287) | MSM offsets (320..327) | batch flag (336..339)
     CK(c, cudaMemcpyAsync(c->rp_tstate.p, stage, 512, cudaMemcpyHostToDevice, s));
+    CK(c, cudaEventRecord(c->stage_ev[slot], s));
     uint8_t *d_par = c->rp_tstate.as<uint8_t>();
     const uint8_t *d_tstate = d_par, *d_seed = d_par + 256;
     uint32_t *d_offsets = reinterpret_cast<uint32_t *>(d_par + 320), *d_batch_ok = reinterpret_cast<uint32_t *>(d_par + 336);

@@ -141,7 +141,10 @@ int bp_rangeproof_verify_begin(bp_ctx *ctx, bp_gens *gens, const uint8_t transcr
                                size_t n, size_t m, size_t count, const uint8_t seed[32]);
 int bp_rangeproof_verify_finish(bp_ctx *ctx, uint8_t *verdicts);
 /* Device-resident form: proofs/commitments are device pointers; verdicts stay on the device
- * (count x uint32).  Used for the HBM-resident throughput measurement. */
+ * (count x uint32) and nothing is synchronised, so calls can be queued back to back on one context.
+ * There is no per-proof recheck on this path: if the combined check fails, every well-formed proof of the
+ * batch is marked BP_PROOF_VERIFICATION_ERROR and *h_batch_ok_pinned (optional, pinned) becomes 0 — rerun such a
+ * batch through bp_rangeproof_verify_batch for per-proof verdicts.  Used for the HBM-resident throughput measurement. */
 int bp_rangeproof_verify_batch_device(bp_ctx *ctx, bp_gens *gens, const uint8_t transcript[BP_TRANSCRIPT_BYTES],
                                       const void *d_proofs, size_t proof_len, const void *d_commitments,
                                       size_t n, size_t m, size_t count, const uint8_t seed[32], void *d_verdicts_u32,

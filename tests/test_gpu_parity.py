@@ -260,3 +260,29 @@ def test_differential_fuzz_against_oracle(gpu_ctx, orc):
         got = bp.verify_batch(gpu_ctx, gens, t, bytes(pb), bytes(vb), n, m, count, seed=bytes([round_]) * 32)
         assert got == want, (round_, [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w])
     gens.close()
+
+
+def test_back_to_back_device_calls_keep_their_own_parameters(gpu_ctx, orc):
+    """bp_rangeproof_verify_batch_device returns without synchronising: calls queued back to back on one context must each use the
+    transcript they were given (their parameter blocks travel through a pinned staging ring), not the last caller's."""
+    import torch
+    import bulletproofs_b200 as bp
+    n, m, count = 32, 1, 16
+    rnd = random.Random(31)
+    og = orc.gens(n, m); gens = bp.Gens(gpu_ctx, n, m)
+    vals = [rnd.randrange(1 << n) for _ in range(count)]; bl = b"".join(le(rnd.randrange(l)) for _ in range(count))
+    seeds = b"".join(i.to_bytes(8, "little") + bytes(24) for i in range(count))
+    proofs, Vs = orc.prove_many(og, orc.transcript(b"label A"), vals, bl, n, m, seeds, nthreads=2)
+    d_proofs = torch.frombuffer(bytearray(proofs), dtype=torch.uint8).cuda(); d_vs = torch.frombuffer(bytearray(Vs), dtype=torch.uint8).cuda()
+    rounds = 24                                     # more than the ring has slots
+    d_verdicts = torch.full((rounds, count), 77, dtype=torch.int32, device="cuda")
+    good = bp.BatchVerifier(gpu_ctx, gens, bp.Transcript(b"label A"), n, m, count)
+    wrong = bp.BatchVerifier(gpu_ctx, gens, bp.Transcript(b"label B"), n, m, count)      # same proofs under another transcript: the combined check fails,
+    torch.cuda.synchronize()                                                              # and the device path (no per-proof recheck) marks the whole batch
+    for r in range(rounds):
+        (good if r % 2 == 0 else wrong).run_device(d_proofs.data_ptr(), d_vs.data_ptr(), d_verdicts[r].data_ptr(), None)
+    gpu_ctx.synchronize()
+    got = d_verdicts.cpu().tolist()
+    for r in range(rounds):
+        assert got[r] == [0 if r % 2 == 0 else 1] * count, (r, got[r])
+    gens.close()

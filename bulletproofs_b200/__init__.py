@@ -44,6 +44,10 @@ SYMBOLS = {
     "bp_rangeproof_verify_begin": (_int, [_vp, _vp, _u8p, _vp, _sz, _vp, _sz, _sz, _sz, _u8p]),
     "bp_rangeproof_verify_finish": (_int, [_vp, _u8p]),
     "bp_rangeproof_verify_batch_device": (_int, [_vp, _vp, _u8p, _vp, _sz, _vp, _sz, _sz, _sz, _u8p, _vp, _vp]),
+    "bp_rangeproof_verify_group_begin": (_int, [_vp, _vp, _u8p, _vp, _sz, _vp, _sz, _sz, _sz, _sz, _u8p]),
+    "bp_rangeproof_verify_group_finish": (_int, [_vp, _u8p, _u8p]),
+    "bp_rangeproof_verify_group_device": (_int, [_vp, _vp, _u8p, _vp, _sz, _vp, _sz, _sz, _sz, _sz, _u8p, _vp, _vp]),
+    "bp_rangeproof_verify_reserve": (_int, [_vp, _vp, _sz, _sz, _sz, _sz]),
     "bp_gens_table_export": (_int, [_vp, _vp]),
     "bp_gens_table_import": (_int, [_vp, _vp]),
     "bp_prof_enable": (_int, [_vp, _int]),
@@ -308,31 +312,37 @@ class Gens:
 
 
 class BatchVerifier:
-    """Pipelined form of the batch verifier over raw buffers (bench.py): `begin` queues the H2D copies, kernels
-    and the verdict D2H on the context's stream, `finish` synchronises and returns the verdict codes."""
+    """Pipelined form of the batch verifier over raw buffers (bench.py): `n_batches` independent batches of `count` proofs per
+    launch group.  The constructor reserves the geometry on the context (arenas sized, launch sequence captured as a CUDA graph,
+    one warm pass) so that no later call allocates.  `begin` queues the H2D copies, the graph and the verdict D2H on the
+    context's stream, `finish` synchronises and returns (verdict codes, per-batch accept flags)."""
 
-    def __init__(self, ctx: Context, gens: Gens, transcript: Transcript, n: int, m: int, count: int):
-        self.ctx, self.gens, self.n, self.m, self.count = ctx, gens, n, m, count
+    def __init__(self, ctx: Context, gens: Gens, transcript: Transcript, n: int, m: int, count: int, n_batches: int = 1, reserve: bool = True):
+        self.ctx, self.gens, self.n, self.m, self.count, self.n_batches = ctx, gens, n, m, count, n_batches
         self.t = transcript.to_bytes()
         self.proof_len = rangeproof_size(n, m)
-        self._verdicts = ctypes.create_string_buffer(count)
+        self._verdicts = ctypes.create_string_buffer(count * n_batches)
+        self._batch_ok = ctypes.create_string_buffer(n_batches)
         self.busy = False
+        if reserve:
+            ctx._check(lib().bp_rangeproof_verify_reserve(ctx._h, gens._h, n, m, count, n_batches))
 
     def begin(self, proofs_ptr: int, commitments_ptr: int, seed: bytes = None):
         """proofs_ptr / commitments_ptr: host addresses (pinned memory for truly asynchronous copies)."""
-        self.ctx._check(lib().bp_rangeproof_verify_begin(self.ctx._h, self.gens._h, self.t, proofs_ptr, self.proof_len, commitments_ptr,
-                                                         self.n, self.m, self.count, seed))
+        self.ctx._check(lib().bp_rangeproof_verify_group_begin(self.ctx._h, self.gens._h, self.t, proofs_ptr, self.proof_len, commitments_ptr,
+                                                               self.n, self.m, self.count, self.n_batches, seed))
         self.busy = True
 
     def finish(self):
-        self.ctx._check(lib().bp_rangeproof_verify_finish(self.ctx._h, self._verdicts))
+        self.ctx._check(lib().bp_rangeproof_verify_group_finish(self.ctx._h, self._verdicts, self._batch_ok))
         self.busy = False
+        self.batch_ok = list(self._batch_ok.raw)
         return self._verdicts.raw
 
     def run_device(self, d_proofs: int, d_commitments: int, d_verdicts_u32: int, h_batch_ok_pinned: int = None, seed: bytes = None):
         """device-resident inputs; nothing is synchronised (verdicts stay on the device)."""
-        self.ctx._check(lib().bp_rangeproof_verify_batch_device(self.ctx._h, self.gens._h, self.t, d_proofs, self.proof_len, d_commitments,
-                                                                self.n, self.m, self.count, seed, d_verdicts_u32, h_batch_ok_pinned))
+        self.ctx._check(lib().bp_rangeproof_verify_group_device(self.ctx._h, self.gens._h, self.t, d_proofs, self.proof_len, d_commitments,
+                                                                self.n, self.m, self.count, self.n_batches, seed, d_verdicts_u32, h_batch_ok_pinned))
 
 
 def prove_multiple(ctx: Context, gens: Gens, transcript: Transcript, values, blindings: bytes, n: int, rng_seed: bytes):
@@ -405,6 +415,17 @@ def verify_batch(ctx: Context, gens: Gens, transcript: Transcript, proofs: bytes
     verdicts = ctypes.create_string_buffer(count)
     ctx._check(lib().bp_rangeproof_verify_batch(ctx._h, gens._h, transcript.to_bytes(), proofs, proof_len, commitments, n, m, count, seed, verdicts))
     return list(verdicts.raw)
+
+
+def verify_group(ctx: Context, gens: Gens, transcript: Transcript, proofs: bytes, commitments: bytes, n: int, m: int, count: int, n_batches: int, seed: bytes = None):
+    """`n_batches` independent batches of `count` proofs in one launch group; returns (per-proof verdict codes, per-batch accept flags)."""
+    proof_len = rangeproof_size(n, m)
+    if len(proofs) != proof_len * count * n_batches or len(commitments) != 32 * m * count * n_batches:
+        raise BpError(ERR_LENGTH_MISMATCH, "proof/commitment buffer sizes")
+    verdicts = ctypes.create_string_buffer(count * n_batches); ok = ctypes.create_string_buffer(n_batches)
+    ctx._check(lib().bp_rangeproof_verify_group_begin(ctx._h, gens._h, transcript.to_bytes(), proofs, proof_len, commitments, n, m, count, n_batches, seed))
+    ctx._check(lib().bp_rangeproof_verify_group_finish(ctx._h, verdicts, ok))
+    return list(verdicts.raw), list(ok.raw)
 
 
 # ---- aggregated range-proof MPC (bulletproofs_b200/host/mpc.{hpp,cpp}: Party / Dealer typestates of src/range_proof/{party,dealer,messages}.rs).

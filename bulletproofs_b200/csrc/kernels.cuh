@@ -450,37 +450,45 @@ __global__ void k_gather_niels(const ge_niels *__restrict__ table, const uint32_
 }
 
 // ------------------------------------------------------------------ range-proof batch verification kernels
-struct rp_geom { uint32_t n, m, k, N, D, S; uint32_t proof_len; };   // D = 4+2k+m dynamic terms, S = 2+2N static terms
+// One launch group verifies `nbatch` independent batches of `count` proofs each: every batch has its own random-linear-
+// combination MSM of T = S + count*D terms and its own accept flag; the per-proof kernels run over all nbatch*count proofs.
+struct rp_geom { uint32_t n, m, k, N, D, S; uint32_t proof_len; uint32_t count, nbatch, T; };   // D = 4+2k+m dynamic terms, S = 2+2N static terms
 
-// K6: transcript replay + the sequential head of the scalar assembly.  One thread per proof (32 proofs
-// per warp, identical control flow, every lane busy); the STROBE state of each thread is a padded
-// shared-memory row (stride 204 B: conflict-free byte access).  Writes one rp_head per proof.
+// Per-call parameter block, uploaded through a pinned staging ring; kernels read the input addresses from it so that the
+// launch sequence itself is the same for every call on a reserved geometry (captured once as a CUDA graph).
+struct rp_params {
+    uint8_t tstate[208];                       // serialized transcript (BP_TRANSCRIPT_BYTES used)
+    uint8_t seed[32];                          // external randomness of the batching weights
+    const uint8_t *proofs, *commitments;       // device addresses: nbatch*count proofs / nbatch*count*m commitments
+    uint32_t *verdict;                         // device address: nbatch*count verdict codes
+    uint8_t pad_[512 - 208 - 32 - 24];
+};
+static_assert(sizeof(rp_params) == 512, "parameter block");
+
+__device__ __forceinline__ uint32_t rp_eff_status(uint32_t st, uint32_t dec_bad) {          // an undecodable point is a VerificationError (mod.rs:445)
+    return st != BP_PROOF_OK ? st : (dec_bad ? (uint32_t)BP_PROOF_VERIFICATION_ERROR : (uint32_t)BP_PROOF_OK);
+}
+
+// K6: transcript replay (pure hashing).  One thread per proof (32 proofs per warp, identical control flow, every lane busy);
+// the STROBE state of each thread is a padded shared-memory row (stride 204 B: conflict-free byte access).
 #define RP_TR_THREADS 32
-__global__ void __launch_bounds__(RP_TR_THREADS) k_rp_transcript(const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ commitments, rp_geom g,
-                                                                   const uint8_t *__restrict__ tstate, const uint8_t *__restrict__ seed, uint32_t count,
+__global__ void __launch_bounds__(RP_TR_THREADS) k_rp_transcript(const rp_params *__restrict__ par, rp_geom g, uint32_t total,
                                                                    uint8_t *__restrict__ raw, uint32_t *__restrict__ status) {
     __shared__ __align__(16) uint8_t rows[RP_TR_THREADS][204];
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= count) return;
-    const uint8_t *proof = proofs + (size_t)p * g.proof_len, *V = commitments + (size_t)p * g.m * 32;
+    if (p >= total) return;
+    const uint8_t *proof = par->proofs + (size_t)p * g.proof_len, *V = par->commitments + (size_t)p * g.m * 32;
     uint8_t (*my)[64] = reinterpret_cast<uint8_t (*)[64]>(raw + (size_t)p * (RP_RAW_U + g.k) * 64);
-    // per-proof batching weights: Keccak-f PRF keyed by the 32-byte seed, domain-separated by the proof index
-    uint64_t st[25];
-    for (int i = 0; i < 25; i++) st[i] = 0;
-    for (int i = 0; i < 4; i++) { uint64_t wv = 0; for (int j = 0; j < 8; j++) wv |= (uint64_t)seed[8 * i + j] << (8 * j); st[i] = wv; }
-    st[4] = p; st[5] = 0x62702d7765696768ULL;  /* "bp-weigh" */ st[16] ^= 0x8000000000000000ULL;
-    keccak_f1600(st);
-    uint64_t *wout = reinterpret_cast<uint64_t *>(my[RP_RAW_C]);      // c = wide(st[0..8)), rho = wide(st[8..16)); rows are 64-byte aligned
-    for (int i = 0; i < 16; i++) wout[i] = st[i];
-    status[p] = rp_transcript_raw(my, proof, g.k, V, g.n, g.m, tstate, rows[threadIdx.x]);
+    status[p] = rp_transcript_raw(my, proof, g.k, V, g.n, g.m, par->tstate, par->seed, rows[threadIdx.x]);
 }
 // Cooperative head: the ~180 Montgomery products of one proof's shared scalars and tables (rp_scalars_head is the sequential
 // statement of the same values) are split over RP_HEAD_WARPS warps; lane = proof, so every warp runs one straight-line task
 // for 32 proofs and the block synchronises between the four dependency phases.  Writes heads[p] and the proof's tables.
 #define RP_HEAD_WARPS 8
-__global__ void __launch_bounds__(32 * RP_HEAD_WARPS) k_rp_head(const uint8_t *__restrict__ proofs, rp_geom g, const uint8_t *__restrict__ raw, uint32_t count,
+__global__ void __launch_bounds__(32 * RP_HEAD_WARPS) k_rp_head(const rp_params *__restrict__ par, rp_geom g, const uint8_t *__restrict__ raw, uint32_t count,
                                                                rp_head *__restrict__ heads, sc *__restrict__ tabs, const sc *__restrict__ pow2,
                                                                rp_work *__restrict__ work, uint32_t *__restrict__ status) {
+    const uint8_t *proofs = par->proofs;
     const uint32_t lane = threadIdx.x & 31, wq = threadIdx.x >> 5, p = blockIdx.x * 32 + lane;
     const bool in = p < count;
     const uint32_t pc = in ? p : count - 1;
@@ -564,51 +572,53 @@ __global__ void __launch_bounds__(32 * RP_HEAD_WARPS) k_rp_head(const uint8_t *_
 }
 // K5: verification scalars, fully data-parallel: one thread per (proof, term) with term in
 // [0, N) -> (g_i, h_i) and [N, N + D) -> the per-proof scalars.
-//   contrib : count x S Montgomery scalars (weighted static-term scalars: B~, B, G.., H..)
-//   dyn     : count x D canonical scalars, written straight into the MSM scalar array
-__global__ void __launch_bounds__(128) k_rp_scalars(rp_geom g, const rp_head *__restrict__ heads, const sc *__restrict__ tabs, uint32_t count,
-                                                    sc *__restrict__ contrib, uint8_t *__restrict__ dyn_scalars) {
+//   contrib : total x S Montgomery scalars (weighted static-term scalars: B~, B, G.., H..)
+//   scal    : nbatch x T canonical scalars, the MSM scalar arrays; the D scalars of proof q of batch b start at b*T + S + q*D
+// A proof that is malformed or has an undecodable point contributes nothing to its batch's combination.
+__global__ void __launch_bounds__(128) k_rp_scalars(rp_geom g, const rp_head *__restrict__ heads, const sc *__restrict__ tabs, const uint32_t *__restrict__ dec_bad,
+                                                    uint32_t total, sc *__restrict__ contrib, uint8_t *__restrict__ scal) {
     uint32_t per = g.N + g.D;
     size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= (size_t)count * per) return;
+    if (gi >= (size_t)total * per) return;
     uint32_t p = (uint32_t)(gi / per), i = (uint32_t)(gi % per);
     const rp_head &h = heads[p];
     sc *my = contrib + (size_t)p * g.S;
-    uint8_t *dyn = dyn_scalars + (size_t)p * g.D * 32;
-    bool ok = h.status == BP_PROOF_OK;        // a malformed proof contributes nothing to the combination
+    bool ok = h.status == BP_PROOF_OK && !dec_bad[p];
     if (i < g.N) {
         sc gg = sc_zero(), hh = sc_zero();
         if (ok) rp_scalars_gh(h, tabs + (size_t)p * rp_tab_size(g.k, g.m), i, g.k, gg, hh);
         my[2 + i] = gg; my[2 + g.N + i] = hh;
         if (i == 0) { my[0] = ok ? h.blinding_scalar : sc_zero(); my[1] = ok ? h.basepoint_scalar : sc_zero(); }
     } else {
-        uint32_t d = i - g.N;
+        uint32_t d = i - g.N, b = p / g.count, q = p % g.count;
         sc v = ok ? sc_from_mont(rp_scalars_dynamic(h, d, g.k)) : sc_zero();
-        uint8_t b[32]; sc_store(b, v); st32(dyn + 32 * d, b);
+        uint8_t bytes[32]; sc_store(bytes, v); st32(scal + ((size_t)b * g.T + g.S + (size_t)q * g.D + d) * 32, bytes);
     }
 }
-// decompress the per-proof points in MSM order A,S,T_1,T_2,L..,R..,V.. straight out of the proof bytes
-__global__ void __launch_bounds__(128, 5) k_rp_decompress(const uint8_t *__restrict__ proofs, const uint8_t *__restrict__ commitments, rp_geom g, uint32_t count,
-                                                       ge_niels *__restrict__ out, uint32_t *__restrict__ status) {
+// decompress the per-proof points in MSM order A,S,T_1,T_2,L..,R..,V.. straight out of the proof bytes; independent of the
+// transcript, so it runs beside k_rp_transcript / k_rp_head (second branch of the launch graph)
+__global__ void __launch_bounds__(128, 5) k_rp_decompress(const rp_params *__restrict__ par, rp_geom g, uint32_t total,
+                                                       ge_niels *__restrict__ out, uint32_t *__restrict__ dec_bad) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)count * g.D) return;
+    if (i >= (size_t)total * g.D) return;
     uint32_t p = (uint32_t)(i / g.D), idx = (uint32_t)(i % g.D);
-    const uint8_t *proof = proofs + (size_t)p * g.proof_len, *src;
+    const uint8_t *proof = par->proofs + (size_t)p * g.proof_len, *src;
     if (idx < 4) src = proof + 32 * idx;
     else if (idx < 4 + g.k) src = proof + 224 + 64 * (idx - 4);
     else if (idx < 4 + 2 * g.k) src = proof + 224 + 64 * (idx - 4 - g.k) + 32;
-    else src = commitments + ((size_t)p * g.m + (idx - 4 - 2 * g.k)) * 32;
+    else src = par->commitments + ((size_t)p * g.m + (idx - 4 - 2 * g.k)) * 32;
     uint8_t s[32]; ld32_any(s, src);
     fe x, y; bool valid = ge_decode(x, y, s);
     st_niels(out + i, valid ? ge_to_niels_affine(x, y) : ge_niels_identity());
-    if (!valid) atomicCAS(status + p, (uint32_t)BP_PROOF_OK, (uint32_t)BP_PROOF_VERIFICATION_ERROR);
+    if (!valid) dec_bad[p] = 1u;
 }
-// sum the weighted static-term scalars over the proofs of the batch: one block per static term
-__global__ void __launch_bounds__(128) k_rp_static_reduce(const sc *__restrict__ contrib, uint32_t S, uint32_t count, uint8_t *__restrict__ out_scalars) {
+// sum the weighted static-term scalars over the proofs of a batch: one block per (static term, batch)
+__global__ void __launch_bounds__(128) k_rp_static_reduce(const sc *__restrict__ contrib, rp_geom g, uint8_t *__restrict__ scal) {
     __shared__ sc sm[4];
-    uint32_t s = blockIdx.x;
+    uint32_t s = blockIdx.x, b = blockIdx.y;
+    const sc *mine = contrib + (size_t)b * g.count * g.S;
     sc acc = sc_zero();
-    for (uint32_t p = threadIdx.x; p < count; p += blockDim.x) acc = sc_add(acc, contrib[(size_t)p * S + s]);
+    for (uint32_t p = threadIdx.x; p < g.count; p += blockDim.x) acc = sc_add(acc, mine[(size_t)p * g.S + s]);
     for (int d = 16; d >= 1; d >>= 1) {
         sc o; for (int i = 0; i < 8; i++) o.v[i] = __shfl_down_sync(0xffffffffu, acc.v[i], d);
         acc = sc_add(acc, o);
@@ -617,10 +627,11 @@ __global__ void __launch_bounds__(128) k_rp_static_reduce(const sc *__restrict__
     __syncthreads();
     if (threadIdx.x == 0) {
         for (uint32_t k = 1; k < (blockDim.x >> 5); k++) acc = sc_add(acc, sm[k]);
-        uint8_t b[32]; sc_store(b, sc_from_mont(acc)); st32(out_scalars + 32 * (size_t)s, b);
+        uint8_t bytes[32]; sc_store(bytes, sc_from_mont(acc)); st32(scal + ((size_t)b * g.T + s) * 32, bytes);
     }
 }
-// fallback: expand contrib (Montgomery) into per-proof canonical scalar rows [S static | D dynamic]
+// fallback: expand contrib (Montgomery) into per-proof canonical scalar rows [S static | D dynamic] for the proofs of one batch;
+// contrib / dyn_scalars point at the batch's first proof
 __global__ void k_rp_expand_scalars(const sc *__restrict__ contrib, const uint8_t *__restrict__ dyn_scalars, rp_geom g, uint32_t count, uint8_t *__restrict__ out) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t row = g.S + g.D;
@@ -631,15 +642,32 @@ __global__ void k_rp_expand_scalars(const sc *__restrict__ contrib, const uint8_
     else ld32(b, dyn_scalars + ((size_t)p * g.D + (t - g.S)) * 32);
     st32(out + 32 * i, b);
 }
-// final verdicts.  mode 0 (combined check): every proof with status OK inherits the batch result
-// flags[0]; mode 1 (per-proof check): flags[p].
-__global__ void k_rp_verdict(const uint32_t *__restrict__ status, const uint32_t *__restrict__ flags, int per_proof, uint32_t count,
-                             uint32_t *__restrict__ verdict, uint32_t *__restrict__ batch_ok) {
+// final verdicts of the combined check, one block per batch: the batch's MSM result must lie in the identity coset
+// (mod.rs:447); every well-formed proof inherits that result, malformed ones keep their own code; batch_ok[b] = all accepted
+__global__ void __launch_bounds__(256) k_rp_verdict_batch(const uint32_t *__restrict__ status, const uint32_t *__restrict__ dec_bad, const ge_ext *__restrict__ results,
+                                                          rp_geom g, const rp_params *__restrict__ par, uint32_t *__restrict__ batch_ok, uint32_t *__restrict__ combined_ok) {
+    __shared__ uint32_t s_ok, s_all;
+    uint32_t b = blockIdx.x;
+    if (threadIdx.x == 0) { s_ok = ge_is_identity(ld_ext(results + b)) ? 1u : 0u; s_all = 1u; }
+    __syncthreads();
+    uint32_t ok = s_ok, all = 1u;
+    uint32_t *verdict = par->verdict;
+    for (uint32_t q = threadIdx.x; q < g.count; q += blockDim.x) {
+        uint32_t p = b * g.count + q;
+        uint32_t st = rp_eff_status(status[p], dec_bad[p]);
+        uint32_t v = st != BP_PROOF_OK ? st : (ok ? (uint32_t)BP_PROOF_OK : (uint32_t)BP_PROOF_VERIFICATION_ERROR);
+        verdict[p] = v;
+        if (v != BP_PROOF_OK) all = 0u;
+    }
+    if (!all) atomicExch(&s_all, 0u);
+    __syncthreads();
+    if (threadIdx.x == 0) { batch_ok[b] = s_all; combined_ok[b] = s_ok; }       // combined_ok = 0: the per-proof recheck has to find the offenders
+}
+// per-proof verdicts after the fallback MSMs (one result per proof); arrays point at the batch's first proof
+__global__ void k_rp_verdict_proofs(const uint32_t *__restrict__ status, const uint32_t *__restrict__ dec_bad, const ge_ext *__restrict__ results, uint32_t count,
+                                    uint32_t *__restrict__ verdict) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= count) return;
-    uint32_t st = status[p];
-    uint32_t ok = per_proof ? flags[p] : flags[0];
-    uint32_t v = st != BP_PROOF_OK ? st : (ok ? BP_PROOF_OK : BP_PROOF_VERIFICATION_ERROR);
-    verdict[p] = v;
-    if (!per_proof && v != BP_PROOF_OK) atomicExch(batch_ok, 0u);   // combined check failed or a proof was malformed
+    uint32_t st = rp_eff_status(status[p], dec_bad[p]);
+    verdict[p] = st != BP_PROOF_OK ? st : (ge_is_identity(ld_ext(results + p)) ? (uint32_t)BP_PROOF_OK : (uint32_t)BP_PROOF_VERIFICATION_ERROR);
 }

@@ -44,7 +44,7 @@ BP_HD sc rp_challenge(merlin_t &t, const char *label) { uint8_t buf[64]; merlin_
 
 // Transcript replay of one proof: pure hashing.  proof = 32*(9+2k) bytes, V = m*32 bytes, tstate = the serialized
 // transcript the caller passed in, state200 = 200 bytes of 4-byte-aligned scratch for the STROBE state.
-// Output: the 64-byte challenge outputs in the order y, z, x, w, (c, rho: filled by the caller from the weights), u_0..u_{k-1}
+// Output: the 64-byte challenge outputs in the order y, z, x, w, c, rho (the batching weights), u_0..u_{k-1}
 // -> raw[RP_RAW_U + j]; nothing the verifier hashes depends on a challenge, so the reduction mod l is left to the caller.
 #define RP_RAW_Y 0
 #define RP_RAW_Z 1
@@ -55,7 +55,7 @@ BP_HD sc rp_challenge(merlin_t &t, const char *label) { uint8_t buf[64]; merlin_
 #define RP_RAW_U 6
 BP_HD void rp_raw_challenge(merlin_t &t, const char *label, uint8_t *out64) { merlin_challenge(t, label, out64, 64); }
 BP_HDN uint32_t rp_transcript_raw(uint8_t (*raw)[64], const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t n, uint32_t m,
-                                  const uint8_t *tstate, uint8_t *state200) {
+                                  const uint8_t *tstate, const uint8_t *seed, uint8_t *state200) {
     const uint8_t *A = proof, *S = proof + 32, *T1 = proof + 64, *T2 = proof + 96;
     const uint8_t *LR = proof + 224, *ab = proof + 224 + 64 * k;
     // RangeProof::from_bytes / InnerProductProof::from_bytes canonicity (mod.rs:519-524, inner_product_proof.rs:399-404)
@@ -80,14 +80,23 @@ BP_HDN uint32_t rp_transcript_raw(uint8_t (*raw)[64], const uint8_t *proof, uint
         merlin_append(t, "L", LR + 64 * j, 32); merlin_append(t, "R", LR + 64 * j + 32, 32);
         rp_raw_challenge(t, "u", raw[RP_RAW_U + j]);
     }
+    // Batching weights c (mod.rs:396) and rho (row A6): bound to everything the proof's transcript has absorbed, the way
+    // merlin's TranscriptRng binds a prover's randomness -- build_rng() (fork of the state), finalize(rng) = meta_ad("rng") +
+    // KEY(32 bytes of the external RNG: the batch seed), fill_bytes(128) = meta_ad(LE32(128)) + PRF.  A caller that passes a
+    // fixed or known seed therefore still gives a prover no knowledge of the weights before the proof bytes are fixed.
+    strobe_begin_op(t, 16 | 2); strobe_absorb(t, (const uint8_t *)"rng", 3);
+    strobe_begin_op(t, 2 | 4); strobe_overwrite(t, seed, 32);
+    const uint8_t l128[4] = {128, 0, 0, 0};
+    strobe_begin_op(t, 16 | 2); strobe_absorb(t, l128, 4);
+    strobe_begin_op(t, 1 | 2 | 4); strobe_squeeze(t, raw[RP_RAW_C], 128);           // rows C and RHO are adjacent
     return bad ? BP_PROOF_VERIFICATION_ERROR : BP_PROOF_OK;
 }
 // Sequential form (host emulation, reference for the cooperative device head): replay + reduction of the challenges.
-// weights = 128 bytes of per-proof randomness (c, rho).
+// seed = the batch's 32 bytes of external randomness (c and rho are derived from it and the proof's transcript).
 BP_HDN void rp_transcript(rp_challenges &ch, const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t n, uint32_t m,
-                         const uint8_t *tstate, const uint8_t *weights, uint8_t *state200) {
+                         const uint8_t *tstate, const uint8_t *seed, uint8_t *state200) {
     uint8_t raw[RP_RAW_U + BP_MAX_LG_N][64];
-    ch.status = rp_transcript_raw(raw, proof, k, V, n, m, tstate, state200);
+    ch.status = rp_transcript_raw(raw, proof, k, V, n, m, tstate, seed, state200);
     if (ch.status != BP_PROOF_OK) return;
     ch.y = rp_wide(raw[RP_RAW_Y]); ch.z = rp_wide(raw[RP_RAW_Z]); ch.x = rp_wide(raw[RP_RAW_X]); ch.w = rp_wide(raw[RP_RAW_W]);
     for (uint32_t j = 0; j < k; j++) ch.u[j] = rp_wide(raw[RP_RAW_U + j]);
@@ -97,7 +106,7 @@ BP_HDN void rp_transcript(rp_challenges &ch, const uint8_t *proof, uint32_t k, c
     bool bad = sc_is_zero(ch.y);
     for (uint32_t j = 0; j < k; j++) bad = bad || sc_is_zero(ch.u[j]);
     if (bad) { ch.status = BP_PROOF_VERIFICATION_ERROR; return; }
-    ch.c = rp_wide(weights); ch.rho = rp_wide(weights + 64);
+    ch.c = rp_wide(raw[RP_RAW_C]); ch.rho = rp_wide(raw[RP_RAW_RHO]);
     if (sc_is_zero(ch.rho)) ch.rho = sc_mont_one();                  // a zero weight (probability 2^-252) would skip the proof
 }
 

@@ -128,8 +128,10 @@ int bp_gens_create_empty(bp_ctx *ctx, size_t gens_capacity, size_t party_capacit
  * (range_proof/mod.rs:345-452) would: verdict[i] = BP_PROOF_OK iff the reference returns Ok(()).
  * All proofs start from the same transcript state.  Internally one random-linear-combination
  * MSM covers the whole batch; if it does not vanish, every proof is re-checked on its own.
- * seed: 32 bytes of randomness for the batching weights (the reference's `Scalar::random(rng)`,
- * mod.rs:396), or NULL to draw from the OS. */
+ * seed: 32 bytes of external randomness for the batching weights, or NULL to draw from the OS.  The weights of a proof
+ * (the reference's `c = Scalar::random(rng)`, mod.rs:396, and the proof's weight in the combination) are squeezed from a fork
+ * of that proof's final transcript state keyed with the seed -- merlin's `build_rng().finalize(rng)` construction -- so they are
+ * bound to the proof bytes even when the caller's seed is fixed or known. */
 int bp_rangeproof_verify_batch(bp_ctx *ctx, bp_gens *gens, const uint8_t transcript[BP_TRANSCRIPT_BYTES],
                                const uint8_t *proofs, size_t proof_len, const uint8_t *commitments,
                                size_t n, size_t m, size_t count, const uint8_t seed[32], uint8_t *verdicts);
@@ -149,6 +151,26 @@ int bp_rangeproof_verify_batch_device(bp_ctx *ctx, bp_gens *gens, const uint8_t 
                                       const void *d_proofs, size_t proof_len, const void *d_commitments,
                                       size_t n, size_t m, size_t count, const uint8_t seed[32], void *d_verdicts_u32,
                                       uint32_t *h_batch_ok_pinned);
+
+/* Launch groups: `n_batches` (<= 256) independent batches of `count` proofs each in ONE launch sequence.  Every batch keeps its own
+ * random-linear-combination MSM, its own accept flag and its own per-proof fallback; only the kernel launches are shared, so that
+ * the grids of a group fill the 148 SMs where a single 1024-proof batch gives most kernels less than one wave.
+ * proofs / commitments / verdicts are laid out batch after batch (n_batches*count entries); batch_ok (optional): n_batches flags,
+ * 1 = every proof of that batch accepted.  The single-batch entry points above are the n_batches = 1 case. */
+int bp_rangeproof_verify_group_begin(bp_ctx *ctx, bp_gens *gens, const uint8_t transcript[BP_TRANSCRIPT_BYTES],
+                                     const uint8_t *proofs, size_t proof_len, const uint8_t *commitments,
+                                     size_t n, size_t m, size_t count, size_t n_batches, const uint8_t seed[32]);
+int bp_rangeproof_verify_group_finish(bp_ctx *ctx, uint8_t *verdicts, uint8_t *batch_ok);
+/* device-resident form (see bp_rangeproof_verify_batch_device); h_batch_ok_pinned (optional, pinned): n_batches x uint32 */
+int bp_rangeproof_verify_group_device(bp_ctx *ctx, bp_gens *gens, const uint8_t transcript[BP_TRANSCRIPT_BYTES],
+                                      const void *d_proofs, size_t proof_len, const void *d_commitments,
+                                      size_t n, size_t m, size_t count, size_t n_batches, const uint8_t seed[32], void *d_verdicts_u32,
+                                      uint32_t *h_batch_ok_pinned);
+/* Reserve a geometry on a context: sizes every arena the verification of n_batches x count (n, m)-proofs touches, builds the
+ * term->point maps, captures the launch sequence as a CUDA graph (two branches: decompression beside transcript replay) and runs
+ * it once.  Afterwards no call with this geometry allocates, and each call costs one parameter upload + one graph launch.
+ * Other geometries still work on the same context (direct launches, arenas grown on demand). */
+int bp_rangeproof_verify_reserve(bp_ctx *ctx, bp_gens *gens, size_t n, size_t m, size_t count, size_t n_batches);
 
 /* D2D copy of the resident table to / from a caller-owned device buffer of bp_gens_device_table() bytes
  * (the Python harness broadcasts a torch tensor with NCCL and imports it on the other ranks). */

@@ -241,8 +241,10 @@ static int ipp_verify(const ipp_view *p, size_t n, merlin *t, const sc *Gf, cons
 static int valid_bitsize(size_t n) { return n == 8 || n == 16 || n == 32 || n == 64; }
 
 /* RangeProof::verify_multiple_with_rng — range_proof/mod.rs:345-452; from_bytes 497-538 */
-static int rp_verify(const bp_gens *bg, const pedersen_gens *pc, merlin *t, const uint8_t *proof, size_t plen,
-                     const uint8_t *V, size_t m, size_t n, chacha_rng *rng) {
+/* the (scalar, point) terms of the mega-check in the reference's order (mod.rs:421-445): A, S, T_1, T_2, L.., R.., B~, B, G.., H.., V..;
+ * *ms_out / *mp_out are malloc'ed (4 + 2k + 2 + 2N + m entries) when the return value is ORC_OK */
+static int rp_verify_terms(const bp_gens *bg, const pedersen_gens *pc, merlin *t, const uint8_t *proof, size_t plen,
+                           const uint8_t *V, size_t m, size_t n, chacha_rng *rng, sc **ms_out, ge **mp_out, size_t *nt_out, int *k_out) {
     if (plen % 32 || plen < 7 * 32) return ORC_FORMAT_ERROR;
     const uint8_t *A = proof, *S = proof + 32, *T1 = proof + 64, *T2 = proof + 96;
     sc t_x, t_x_bl, e_bl;
@@ -301,11 +303,48 @@ static int rp_verify(const bp_gens *bg, const pedersen_gens *pc, merlin *t, cons
     sc_one(&exp_z);
     for (size_t j = 0; j < m; j++) { sc tt; sc_mul(&tt, &c, &zz); sc_mul(&ms[o + j], &tt, &exp_z); bad |= !ge_decode(&mp[o + j], V + 32 * j); sc_mul(&exp_z, &exp_z, &z); }
     o += m;
-    rc = ORC_OK;
-    if (bad) rc = ORC_VERIFICATION_ERROR;                                              /* :445 */
-    else { ge mega; ge_msm_vartime(&mega, ms, mp, nt); if (!ge_is_identity(&mega)) rc = ORC_VERIFICATION_ERROR; }   /* :447-451 */
-    free(s); free(ms); free(mp);
+    free(s);
+    if (bad) { free(ms); free(mp); return ORC_VERIFICATION_ERROR; }                    /* :445 */
+    *ms_out = ms; *mp_out = mp; *nt_out = nt; *k_out = k;
+    return ORC_OK;
+}
+/* RangeProof::verify_multiple_with_rng — range_proof/mod.rs:345-452; from_bytes 497-538 */
+static int rp_verify(const bp_gens *bg, const pedersen_gens *pc, merlin *t, const uint8_t *proof, size_t plen,
+                     const uint8_t *V, size_t m, size_t n, chacha_rng *rng) {
+    sc *ms; ge *mp; size_t nt; int k;
+    int rc = rp_verify_terms(bg, pc, t, proof, plen, V, m, n, rng, &ms, &mp, &nt, &k);
+    if (rc) return rc;
+    ge mega; ge_msm_vartime(&mega, ms, mp, nt); if (!ge_is_identity(&mega)) rc = ORC_VERIFICATION_ERROR;   /* :447-451 */
+    free(ms); free(mp);
     return rc;
+}
+/* Random-linear-combination batch on the CPU (SURVEY.md section 8a row A6 -- the reference has no batch verifier; this is the
+ * apples-to-apples CPU line next to the GPU engine's batch path): every proof's mega-check is multiplied by its own random
+ * 128-bit weight, the weighted scalars of the shared points B~, B, G.., H.. are summed, and ONE variable-time MSM over
+ * 2 + 2N + count*(4 + 2k + m) terms (Pippenger, the dependency's dispatch) must give the identity.  Returns 1 when the whole
+ * chunk is accepted, 0 when some proof is malformed or the combination does not vanish (callers then verify proof by proof). */
+static int rp_verify_rlc_chunk(const bp_gens *bg, const pedersen_gens *pc, const uint8_t *tstate, const uint8_t *proofs, size_t plen,
+                               const uint8_t *Vs, size_t m, size_t n, size_t count, chacha_rng *rng) {
+    size_t N = n * m, S = 2 + 2 * N, cap = S, used = S;
+    sc *as = calloc(S, sizeof(sc)); ge *ap = malloc(S * sizeof(ge));
+    int ok = 1, have_static = 0;
+    for (size_t i = 0; i < count && ok; i++) {
+        merlin t; memcpy(&t, tstate, sizeof t);
+        sc *ms; ge *mp; size_t nt; int k;
+        if (rp_verify_terms(bg, pc, &t, proofs + i * plen, plen, Vs + 32 * m * i, m, n, rng, &ms, &mp, &nt, &k)) { ok = 0; break; }
+        size_t D = 4 + 2 * (size_t)k + m, so = 4 + 2 * (size_t)k;       /* static block starts after A,S,T1,T2,L..,R.. */
+        uint8_t wb[32] = {0}; chacha_fill(rng, wb, 16); wb[0] |= 1;       /* 128-bit non-zero weight */
+        sc rho; sc_from_bytes_mod_order(&rho, wb);
+        if (used + D > cap) { cap = 2 * cap + D; as = realloc(as, cap * sizeof(sc)); ap = realloc(ap, cap * sizeof(ge)); }
+        if (!have_static) { for (size_t j = 0; j < S; j++) ap[j] = mp[so + j]; have_static = 1; }
+        for (size_t j = 0; j < S; j++) { sc w; sc_mul(&w, &rho, &ms[so + j]); sc_add(&as[j], &as[j], &w); }
+        for (size_t j = 0; j < so; j++) { sc_mul(&as[used], &rho, &ms[j]); ap[used++] = mp[j]; }
+        for (size_t j = 0; j < m; j++) { sc_mul(&as[used], &rho, &ms[so + S + j]); ap[used++] = mp[so + S + j]; }
+        free(ms); free(mp);
+    }
+    if (ok) { ge mega; ge_msm_vartime(&mega, as, ap, used); ok = ge_is_identity(&mega); }
+    free(as); free(ap);
+    return ok;
 }
 
 /* RangeProof::prove_multiple_with_rng — range_proof/mod.rs:234-288, restating the single-process
@@ -411,6 +450,32 @@ static int rp_prove(const bp_gens *bg, const pedersen_gens *pc, merlin *t, const
 /* ------------------------------------------------------------------ exported protocol entry points */
 static pedersen_gens g_pc; static int g_pc_ready = 0;
 static const pedersen_gens *default_pc(void) { if (!g_pc_ready) { pedersen_default(&g_pc); g_pc_ready = 1; } return &g_pc; }
+/* MSM backends: "u64" (serial 51-bit limbs, ge.h), "avx2", "ifma" (4-way vector, vec4_*.h), "auto" = fastest the CPU supports.
+ * Returns 0, or -1 when the CPU lacks the instructions.  Not thread-safe: call before starting worker threads. */
+void orc_vec_msm_avx2(ge *out, const sc *scalars, const ge *points, size_t n);
+void orc_vec_msm_ifma(ge *out, const sc *scalars, const ge *points, size_t n);
+int orc_vec_selftest_avx2(const uint8_t *pts, const uint8_t *rnd);
+int orc_vec_selftest_ifma(const uint8_t *pts, const uint8_t *rnd);
+const char *orc_vec_name_avx2(void);
+const char *orc_vec_name_ifma(void);
+static const char *g_backend_name = "u64 (5x 51-bit limbs, serial)";
+static int cpu_has_avx2(void) { __builtin_cpu_init(); return __builtin_cpu_supports("avx2"); }
+static int cpu_has_ifma(void) { __builtin_cpu_init(); return __builtin_cpu_supports("avx512ifma") && __builtin_cpu_supports("avx512vl") && __builtin_cpu_supports("avx2"); }
+int orc_set_backend(const char *name) {
+    ge_init_constants();
+    ge one[1]; sc s1[1]; ge tmp; ge_identity(&one[0]); memset(s1, 0, sizeof s1);
+    if (!strcmp(name, "auto")) name = cpu_has_ifma() ? "ifma" : cpu_has_avx2() ? "avx2" : "u64";
+    if (!strcmp(name, "u64")) { ge_msm_backend = NULL; g_backend_name = "u64 (5x 51-bit limbs, serial)"; return 0; }
+    if (!strcmp(name, "avx2")) { if (!cpu_has_avx2()) return -1; orc_vec_msm_avx2(&tmp, s1, one, 1); ge_msm_backend = orc_vec_msm_avx2; g_backend_name = orc_vec_name_avx2(); return 0; }
+    if (!strcmp(name, "ifma")) { if (!cpu_has_ifma()) return -1; orc_vec_msm_ifma(&tmp, s1, one, 1); ge_msm_backend = orc_vec_msm_ifma; g_backend_name = orc_vec_name_ifma(); return 0; }
+    return -2;
+}
+const char *orc_backend_name(void) { return g_backend_name; }
+int orc_vec_selftest(const char *name, const uint8_t *pts, const uint8_t *rnd) {
+    if (!strcmp(name, "avx2")) return cpu_has_avx2() ? orc_vec_selftest_avx2(pts, rnd) : -1;
+    if (!strcmp(name, "ifma")) return cpu_has_ifma() ? orc_vec_selftest_ifma(pts, rnd) : -1;
+    return -2;
+}
 void orc_init(void) { ge_init_constants(); default_pc(); }
 
 int orc_rangeproof_verify(void *gens, const uint8_t *transcript_state, const uint8_t *proof, size_t plen,
@@ -685,6 +750,18 @@ typedef struct {
 
 static void *batch_worker(void *arg) {
     batch_job *j = arg;
+    if (j->prove == 2) {        /* RLC batches: thread t takes the contiguous chunk t of the proofs, one combined MSM per chunk */
+        size_t per = (j->count + (size_t)j->nthreads - 1) / (size_t)j->nthreads, a = (size_t)j->tid * per, b = a + per < j->count ? a + per : j->count;
+        if (a >= b) return NULL;
+        chacha_rng rng; chacha_seed(&rng, j->seeds); for (int q = 0; q < j->tid; q++) { uint8_t skip[64]; chacha_fill(&rng, skip, 64); }
+        int ok = rp_verify_rlc_chunk(j->bg, default_pc(), j->tstate, j->proofs + a * j->plen, j->plen, j->Vs + 32 * j->m * a, j->m, j->n, b - a, &rng);
+        for (size_t i = a; i < b; i++) {
+            if (ok) { j->verdicts[i] = 0; continue; }
+            merlin t; memcpy(&t, j->tstate, sizeof t);
+            j->verdicts[i] = (uint8_t)rp_verify(j->bg, default_pc(), &t, j->proofs + i * j->plen, j->plen, j->Vs + 32 * i * j->m, j->m, j->n, &rng);
+        }
+        return NULL;
+    }
     for (size_t i = (size_t)j->tid; i < j->count; i += (size_t)j->nthreads) {
         merlin t; memcpy(&t, j->tstate, sizeof t);
         chacha_rng rng; chacha_seed(&rng, j->seeds + 32 * i);
@@ -709,6 +786,12 @@ void orc_rangeproof_verify_many(void *gens, const uint8_t *transcript_state, con
                                 size_t m, size_t n, size_t count, const uint8_t *seeds, int nthreads, uint8_t *status) {
     batch_job j = {0}; j.bg = gens; j.tstate = transcript_state; j.proofs = proofs; j.plen = plen; j.Vs = Vs; j.m = m; j.n = n; j.count = count;
     j.seeds = seeds; j.verdicts = status; j.prove = 0; run_batch(&j, nthreads);
+}
+/* same verdicts through the CPU random-linear-combination batch: nthreads chunks, one combined MSM each, per-proof recheck of a failing chunk */
+void orc_rangeproof_verify_rlc(void *gens, const uint8_t *transcript_state, const uint8_t *proofs, size_t plen, const uint8_t *Vs,
+                               size_t m, size_t n, size_t count, const uint8_t seed[32], int nthreads, uint8_t *status) {
+    batch_job j = {0}; j.bg = gens; j.tstate = transcript_state; j.proofs = proofs; j.plen = plen; j.Vs = Vs; j.m = m; j.n = n; j.count = count;
+    j.seeds = seed; j.verdicts = status; j.prove = 2; run_batch(&j, nthreads);
 }
 void orc_rangeproof_prove_many(void *gens, const uint8_t *transcript_state, const uint64_t *values, const uint8_t *blindings,
                                size_t m, size_t n, size_t count, const uint8_t *seeds, int nthreads, uint8_t *proofs_out, uint8_t *Vs_out, uint8_t *status) {

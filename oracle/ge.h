@@ -265,8 +265,12 @@ static void ge_msm_pippenger(ge *out, const sc *scalars, const ge *points, size_
     free(digits); free(cached); free(buckets);
 }
 
+/* optional vector backend (msm_avx2.c / msm_ifma.c), selected by orc_set_backend in bp_oracle.c; NULL = the serial u64 code below */
+static void (*ge_msm_backend)(ge *out, const sc *scalars, const ge *points, size_t n) = NULL;
+
 /* the dependency's dispatch: Straus below 190 terms, Pippenger from 190 up */
 static void ge_msm_vartime(ge *out, const sc *scalars, const ge *points, size_t n) {
+    if (ge_msm_backend) { ge_msm_backend(out, scalars, points, n); return; }
     if (n == 0) { ge_identity(out); return; }
     if (n < 190) ge_msm_straus(out, scalars, points, n); else ge_msm_pippenger(out, scalars, points, n);
 }

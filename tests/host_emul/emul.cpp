@@ -59,9 +59,9 @@ void emul_transcript_append(uint8_t *ser, const char *label, const uint8_t *msg,
 void emul_transcript_challenge(uint8_t *ser, const char *label, uint8_t *out, uint32_t len) { alignas(8) uint8_t st[200]; merlin_t m; m.st = st; merlin_load(m, ser); merlin_challenge(m, label, out, len); merlin_store(ser, m); }
 
 // full verification-scalar vector of one proof in the order [B~, B, G.., H.. | A,S,T1,T2,L..,R..,V..], canonical bytes
-int emul_rp_scalars(const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t n, uint32_t m, const uint8_t *tstate, const uint8_t *weights, uint8_t *out) {
+int emul_rp_scalars(const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t n, uint32_t m, const uint8_t *tstate, const uint8_t *seed, uint8_t *out) {
     static rp_head h; static rp_challenges ch; alignas(8) uint8_t st[200];
-    rp_transcript(ch, proof, k, V, n, m, tstate, weights, st);
+    rp_transcript(ch, proof, k, V, n, m, tstate, seed, st);
     if (ch.status) return (int)ch.status;
     std::vector<sc> tab(rp_tab_size(k, m)), pow2(64);
     for (int e = 0; e < 64; e++) pow2[e] = sc_mont_from_u64(1ULL << e);

@@ -115,6 +115,26 @@ class Oracle:
         self.L.orc_rangeproof_verify_many(g, tstate, proofs, plen, Vs, m, n, count, seeds or bytes(32 * count), nthreads, st)
         return list(st.raw)
 
+    def verify_rlc(self, g, tstate, proofs, plen, Vs, n, m, count, seed=bytes(32), nthreads=8):
+        """CPU random-linear-combination batch (one combined MSM per thread's chunk, per-proof recheck of a failing chunk)"""
+        self.L.orc_rangeproof_verify_rlc.argtypes = [_vp, _p, _p, _sz, _p, _sz, _sz, _sz, _p, ctypes.c_int, _p]
+        st = ctypes.create_string_buffer(count)
+        self.L.orc_rangeproof_verify_rlc(g, tstate, proofs, plen, Vs, m, n, count, seed, nthreads, st)
+        return list(st.raw)
+
+    # MSM field backends (oracle/vec4_*.h): "u64", "avx2", "ifma", "auto"; process-wide, not thread-safe
+    def set_backend(self, name):
+        self.L.orc_set_backend.argtypes = [_p]
+        return self.L.orc_set_backend(name.encode())
+
+    def backend_name(self):
+        self.L.orc_backend_name.restype = ctypes.c_char_p
+        return self.L.orc_backend_name().decode()
+
+    def vec_selftest(self, name, points4, rnd8):
+        self.L.orc_vec_selftest.argtypes = [_p, _p, _p]
+        return self.L.orc_vec_selftest(name.encode(), points4, rnd8)
+
     # group / scalar helpers
     def msm(self, scalars, points, naive=False):
         o = ctypes.create_string_buffer(32)

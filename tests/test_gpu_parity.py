@@ -286,3 +286,82 @@ def test_back_to_back_device_calls_keep_their_own_parameters(gpu_ctx, orc):
     for r in range(rounds):
         assert got[r] == [0 if r % 2 == 0 else 1] * count, (r, got[r])
     gens.close()
+
+
+def test_launch_groups_match_oracle_per_proof(gpu_ctx, orc):
+    """Several independent batches in one launch group (bp_rangeproof_verify_group_*): per-proof verdicts == oracle, per-batch accept
+    flags right, a damaged proof only sends its own batch through the per-proof recheck; the reserved (CUDA graph) path and the
+    direct-launch path agree."""
+    import bulletproofs_b200 as bp
+    label = b"AggregateRangeProofBenchmark"
+    n, m, count, nb = 64, 1, 40, 5
+    og = orc.gens(64, 1); gens = bp.Gens(gpu_ctx, 64, 1)
+    proofs, Vs = _workload(orc, og, label, n, m, count * nb, seed=515)
+    plen = len(proofs) // (count * nb)
+    t = bp.Transcript(label); ot = orc.transcript(label)
+    got, ok = bp.verify_group(gpu_ctx, gens, t, proofs, Vs, n, m, count, nb)
+    assert got == [0] * (count * nb) and ok == [1] * nb
+    pb, vb = bytearray(proofs), bytearray(Vs)
+    pb[(1 * count + 7) * plen + 300] ^= 1            # batch 1: one bad proof
+    pb[(3 * count + 0) * plen: (3 * count + 0) * plen + 32] = bytes(32)     # batch 3: A = identity encoding (caught before the MSM: combined check still passes)
+    vb[(3 * count + 39) * 32 + 5] ^= 8              # batch 3: wrong commitment on the last proof
+    pb[(4 * count + 3) * plen + 224: (4 * count + 3) * plen + 256] = le(p + 1)      # batch 4: L_0 undecodable
+    want = orc.verify_many(og, ot, bytes(pb), plen, bytes(vb), n, m, count * nb)
+    for reserve in (False, True):
+        if reserve:
+            v = bp.BatchVerifier(gpu_ctx, gens, t, n, m, count, nb)          # reserves: the next calls with this geometry replay the captured graph
+        got, ok = bp.verify_group(gpu_ctx, gens, t, bytes(pb), bytes(vb), n, m, count, nb, seed=bytes([9]) * 32)
+        assert got == want, (reserve, [(i, g, w) for i, (g, w) in enumerate(zip(got, want)) if g != w])
+        assert ok == [1, 0, 1, 0, 0]
+        assert sum(1 for w in want if w) == 4
+    # another geometry on the same (reserved) context takes the direct path and leaves the graph intact
+    assert bp.verify_batch(gpu_ctx, gens, t, proofs[:3 * plen], Vs[:3 * 32], n, m, 3) == [0, 0, 0]
+    got, ok = bp.verify_group(gpu_ctx, gens, t, proofs, Vs, n, m, count, nb)
+    assert got == [0] * (count * nb) and ok == [1] * nb
+    gens.close()
+
+
+def test_other_calls_between_verifications_keep_the_point_map(gpu_ctx, orc):
+    """An indexed MSM (prover, R1CS verifier, MPC audit) on a context must not disturb the verifier's cached term->point map: device-path
+    verification, then prove_multiple on the same context, then device-path verification again, all accepted (round-1 ADVICE, high)."""
+    import torch
+    import bulletproofs_b200 as bp
+    label = b"AggregateRangeProofBenchmark"
+    n, m, count = 32, 1, 24
+    og = orc.gens(n, m); gens = bp.Gens(gpu_ctx, n, m)
+    proofs, Vs = _workload(orc, og, label, n, m, count, seed=808)
+    d_p = torch.frombuffer(bytearray(proofs), dtype=torch.uint8).cuda(); d_v = torch.frombuffer(bytearray(Vs), dtype=torch.uint8).cuda()
+    d_verd = torch.full((3, count), 9, dtype=torch.int32, device="cuda"); h_ok = torch.zeros(3, dtype=torch.int32).pin_memory()
+    ver = bp.BatchVerifier(gpu_ctx, gens, bp.Transcript(label), n, m, count, reserve=False)
+    ver.run_device(d_p.data_ptr(), d_v.data_ptr(), d_verd[0].data_ptr(), h_ok[0:].data_ptr()); gpu_ctx.synchronize()
+    rc, proof, V = bp.prove_multiple(gpu_ctx, gens, bp.Transcript(label), [5], le(7), n, bytes(32))
+    assert rc == 0
+    ver.run_device(d_p.data_ptr(), d_v.data_ptr(), d_verd[1].data_ptr(), h_ok[1:].data_ptr()); gpu_ctx.synchronize()
+    ver2 = bp.BatchVerifier(gpu_ctx, gens, bp.Transcript(label), n, m, count)       # reserved / graph path
+    rc, proof, V = bp.prove_multiple(gpu_ctx, gens, bp.Transcript(label), [6], le(8), n, bytes(32))
+    ver2.run_device(d_p.data_ptr(), d_v.data_ptr(), d_verd[2].data_ptr(), h_ok[2:].data_ptr()); gpu_ctx.synchronize()
+    assert d_verd.cpu().tolist() == [[0] * count] * 3 and h_ok.tolist() == [1, 1, 1]
+    gens.close()
+
+
+def test_pending_verification_blocks_other_entry_points(gpu_ctx, orc):
+    """Between verify_begin and verify_finish the context's arenas belong to the pending verification (its fallback reads them):
+    other entry points fail with a clear error instead of clobbering them, and a failed begin leaves the context usable."""
+    import bulletproofs_b200 as bp
+    label = b"AggregateRangeProofBenchmark"
+    n, m, count = 8, 1, 6
+    og = orc.gens(n, m); gens = bp.Gens(gpu_ctx, n, m)
+    proofs, Vs = _workload(orc, og, label, n, m, count, seed=11)
+    pb = bytearray(proofs); pb[2 * (len(proofs) // count) + 140] ^= 1
+    ver = bp.BatchVerifier(gpu_ctx, gens, bp.Transcript(label), n, m, count, reserve=False)
+    import ctypes
+    hp = ctypes.create_string_buffer(bytes(pb)); hv = ctypes.create_string_buffer(Vs)
+    ver.begin(ctypes.addressof(hp), ctypes.addressof(hv))
+    with pytest.raises(bp.BpError):
+        gpu_ctx.msm(le(1), orc.from_uniform(bytes(64)))
+    with pytest.raises(bp.BpError):
+        ver.begin(ctypes.addressof(hp), ctypes.addressof(hv))
+    got = list(ver.finish())
+    assert [i for i, v in enumerate(got) if v] == [2]
+    assert gpu_ctx.msm(le(1), orc.from_uniform(bytes(64)))[0] == 0
+    gens.close()

@@ -116,11 +116,11 @@ def test_verification_scalars_on_golden_proofs(E, orc, golden):
             pbb = bytearray(pb)
             if tamper: pbb[200] ^= 4
             out = buf(32 * (S + D))
-            assert E.emul_rp_scalars(bytes(pbb), k, vc, n, m, st.raw, rnd.randbytes(128), out) == 0
+            assert E.emul_rp_scalars(bytes(pbb), k, vc, n, m, st.raw, rnd.randbytes(32), out) == 0
             rc, res = orc.msm(out.raw, b"".join(pts))
             assert rc == 0 and (res == bytes(32)) == (not tamper), (n, m, tamper)
     # non-canonical scalar in the proof -> FormatError (2); identity point A -> VerificationError (1)
     pb = bytearray(bytes.fromhex(golden["proofs"][0]["proof"])); pb[128:160] = b"\xff" * 32
-    assert E.emul_rp_scalars(bytes(pb), 3, vc, 8, 1, st.raw, bytes(128), buf(32 * 30)) == 2
+    assert E.emul_rp_scalars(bytes(pb), 3, vc, 8, 1, st.raw, bytes(32), buf(32 * 30)) == 2
     pb = bytearray(bytes.fromhex(golden["proofs"][0]["proof"])); pb[0:32] = bytes(32)
-    assert E.emul_rp_scalars(bytes(pb), 3, vc, 8, 1, st.raw, bytes(128), buf(32 * 30)) == 1
+    assert E.emul_rp_scalars(bytes(pb), 3, vc, 8, 1, st.raw, bytes(32), buf(32 * 30)) == 1

@@ -179,3 +179,43 @@ def test_group_against_libsodium(orc):
     for _ in range(300):
         s = rnd.randbytes(32)
         assert sod.crypto_core_ristretto255_is_valid_point(s) == orc.point_is_valid(s)
+
+
+@pytest.mark.parametrize("backend", ["avx2", "ifma"])
+def test_vector_backends_pinned_like_the_serial_one(orc, golden, backend):
+    """The 4-way vector field backends of the oracle's MSM (oracle/vec4_avx2.h: the reference's default `avx2_backend`,
+    Cargo.toml:41-42; oracle/vec4_ifma.h: README.md:82-84) against the same pins as the serial u64 code: field / point
+    self-test vs the serial code, MSM results identical at Straus and Pippenger sizes, all 16 golden proofs accept,
+    tampered ones reject, the prover's bytes do not depend on the backend."""
+    if orc.set_backend(backend) != 0:
+        orc.set_backend("u64")
+        pytest.skip(f"this CPU has no {backend}")
+    try:
+        rnd = random.Random(11)
+        pts = [orc.from_uniform(rnd.randbytes(64)) for _ in range(48)]
+        edge = [2**255 - 20, 2**255 - 21, 0, 1, 2**255 - 1, 2**254, 2**51 - 1, 19]
+        for t in range(100):
+            r8 = b"".join(x.to_bytes(32, "little") for x in edge) if t == 0 else b"".join(rnd.getrandbits(255).to_bytes(32, "little") for _ in range(8))
+            assert orc.vec_selftest(backend, b"".join(rnd.choice(pts) for _ in range(4)), r8) == 0
+        for n in (1, 2, 3, 17, 147, 189, 190, 499, 500, 800, 2090):
+            sc = b"".join(rnd.randrange(L_ORDER).to_bytes(32, "little") for _ in range(n)); pp = b"".join(rnd.choice(pts) for _ in range(n))
+            got = orc.msm(sc, pp)
+            orc.set_backend("u64"); want = orc.msm(sc, pp); orc.set_backend(backend)
+            assert got == want, n
+        special = b"".join(x.to_bytes(32, "little") for x in (0, 1, L_ORDER - 1, 2**252, 2**128, 5)); pp = b"".join(pts[:6])
+        got = orc.msm(special, pp); orc.set_backend("u64"); assert got == orc.msm(special, pp); orc.set_backend(backend)
+        assert orc.msm((7).to_bytes(32, "little") + (L_ORDER - 7).to_bytes(32, "little"), pts[0] * 2) == (0, bytes(32))
+        g = orc.gens(64, 8)
+        vc = b"".join(bytes.fromhex(v) for v in golden["value_commitments"])
+        t = orc.transcript(golden["transcript_label"].encode())
+        for p in golden["proofs"]:
+            proof = bytes.fromhex(p["proof"])
+            assert orc.rangeproof_verify(g, t, proof, vc[:32 * p["m"]], p["m"], p["n"]) == 0, (backend, p["n"], p["m"])
+            bad = bytearray(proof); bad[rnd.randrange(len(bad))] ^= 1 << rnd.randrange(8)
+            assert orc.rangeproof_verify(g, t, bytes(bad), vc[:32 * p["m"]], p["m"], p["n"]) != 0
+        rc, proof_v, V_v = orc.rangeproof_prove(g, t, [3, 250], (5).to_bytes(32, "little") + (6).to_bytes(32, "little"), 8)
+        orc.set_backend("u64")
+        assert (rc, proof_v, V_v) == orc.rangeproof_prove(g, t, [3, 250], (5).to_bytes(32, "little") + (6).to_bytes(32, "little"), 8) and rc == 0
+        assert "u64" in orc.backend_name()
+    finally:
+        orc.set_backend("u64")

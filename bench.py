@@ -251,6 +251,7 @@ def main():
     ap.add_argument("--workload", default="rangeproof", choices=["rangeproof", "msm"])
     ap.add_argument("--lg", type=int, default=16, help="--workload msm: terms per MSM = 2^lg")
     ap.add_argument("--msms", type=int, default=8, help="--workload msm: MSMs per call")
+    ap.add_argument("--check-lg", type=int, default=16, help="--workload msm: compare the first MSM with the CPU oracle up to this size")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))

@@ -26,6 +26,14 @@ SYMBOLS = {
     "bp_ctx_synchronize": (_int, [_vp]),
     "bp_decompress_check_batch": (_int, [_vp, _u8p, _sz, _u8p]),
     "bp_from_uniform_bytes_batch": (_int, [_vp, _u8p, _sz, _u8p]),
+    "bp_decompress_batch": (_int, [_vp, _u8p, _sz, _u8p, _u8p]),
+    "bp_compress_batch": (_int, [_vp, _u8p, _sz, _u8p]),
+    "bp_points_create": (_int, [_vp, _vp, _sz, _c.POINTER(_vp)]),
+    "bp_points_create_device": (_int, [_vp, _vp, _sz, _c.POINTER(_vp)]),
+    "bp_points_destroy": (None, [_vp]),
+    "bp_points_count": (_sz, [_vp]),
+    "bp_msm_points_device": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp]),
+    "bp_msm_points": (_int, [_vp, _vp, _vp, _sz, _sz, _vp, _vp]),
     "bp_msm": (_int, [_vp, _u8p, _u8p, _sz, _u8p]),
     "bp_msm_batch": (_int, [_vp, _u8p, _u8p, _c.POINTER(_c.c_uint64), _sz, _u8p, _u8p]),
     "bp_msm_batch_device": (_int, [_vp, _vp, _vp, _vp, _sz, _sz, _vp, _vp]),
@@ -35,6 +43,13 @@ SYMBOLS = {
     "bp_ipp_lr": (_int, [_vp, _sz, _u8p, _u8p, _u8p, _u8p]),
     "bp_ipp_fold": (_int, [_vp, _sz, _u8p, _u8p, _u8p, _u8p, _int]),
     "bp_ipp_end": (None, [_vp]),
+    "bp_ippx_begin": (_int, [_vp, _vp, _sz, _sz, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _c.POINTER(_vp)]),
+    "bp_ippx_begin_points": (_int, [_vp, _u8p, _u8p, _sz, _sz, _u8p, _u8p, _u8p, _u8p, _u8p, _c.POINTER(_vp)]),
+    "bp_ippx_current_len": (_sz, [_vp]),
+    "bp_ippx_round": (_int, [_vp, _u8p]),
+    "bp_ippx_fold": (_int, [_vp, _u8p, _u8p]),
+    "bp_ippx_finish": (_int, [_vp, _u8p]),
+    "bp_ippx_end": (None, [_vp]),
     "bp_gens_create": (_int, [_vp, _sz, _sz, _c.POINTER(_vp)]),
     "bp_gens_create_empty": (_int, [_vp, _sz, _sz, _c.POINTER(_vp)]),
     "bp_gens_destroy": (None, [_vp]),
@@ -240,6 +255,19 @@ class Context:
         self._check(lib().bp_from_uniform_bytes_batch(self._h, uniform, n, out))
         return out.raw[:32 * n]
 
+    def decompress(self, points: bytes):
+        """CompressedRistretto::decompress for n points -> (list of 128-byte X|Y|Z|T values, ok flags)"""
+        n = len(points) // 32
+        out = ctypes.create_string_buffer(128 * max(n, 1)); ok = ctypes.create_string_buffer(max(n, 1))
+        self._check(lib().bp_decompress_batch(self._h, points, n, out, ok))
+        return [out.raw[128 * i:128 * i + 128] for i in range(n)], list(ok.raw[:n])
+
+    def compress(self, xyzt: bytes) -> bytes:
+        n = len(xyzt) // 128
+        out = ctypes.create_string_buffer(32 * max(n, 1))
+        self._check(lib().bp_compress_batch(self._h, xyzt, n, out))
+        return out.raw[:32 * n]
+
     # ---- MSM
     def msm(self, scalars: bytes, points: bytes):
         """RistrettoPoint::vartime_multiscalar_mul; returns (status, 32-byte compressed result)."""
@@ -264,6 +292,35 @@ class Context:
         out = ctypes.create_string_buffer(32 * n)
         self._check(lib().bp_debug_fe_op(self._h, op, a, b, n, out))
         return out.raw
+
+
+class PointSet:
+    """n points decompressed once and resident on the device (bp_points): bases of repeated MSMs."""
+
+    def __init__(self, ctx: Context, points=None, n: int = None, device_ptr: int = None):
+        self.ctx, self._h = ctx, _vp()
+        if device_ptr is not None:
+            ctx._check(lib().bp_points_create_device(ctx._h, device_ptr, n, ctypes.byref(self._h)))
+        else:
+            n = len(points) // 32 if n is None else n
+            buf = ctypes.create_string_buffer(bytes(points), 32 * n) if isinstance(points, (bytes, bytearray)) else None
+            ctx._check(lib().bp_points_create(ctx._h, ctypes.addressof(buf) if buf is not None else points, n, ctypes.byref(self._h)))
+        self.n = n
+
+    def msm(self, scalars: bytes, n_msm: int, terms: int):
+        """n_msm MSMs of `terms` terms over the first `terms` points; returns (status list, list of 32-byte results)"""
+        outs = ctypes.create_string_buffer(32 * n_msm); st = ctypes.create_string_buffer(n_msm)
+        buf = ctypes.create_string_buffer(bytes(scalars), 32 * n_msm * terms)
+        self.ctx._check(lib().bp_msm_points(self.ctx._h, self._h, ctypes.addressof(buf), n_msm, terms, ctypes.addressof(outs), ctypes.addressof(st)))
+        return list(st.raw), [outs.raw[32 * i:32 * i + 32] for i in range(n_msm)]
+
+    def msm_device(self, d_scalars: int, n_msm: int, terms: int, d_outs: int, d_status: int = None):
+        self.ctx._check(lib().bp_msm_points_device(self.ctx._h, self._h, d_scalars, n_msm, terms, d_outs, d_status))
+
+    def close(self):
+        if self._h:
+            lib().bp_points_destroy(self._h)
+            self._h = _vp()
 
 
 class Gens:

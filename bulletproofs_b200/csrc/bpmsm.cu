@@ -30,9 +30,9 @@ struct DevBuf {
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
-enum KernelId { KID_DECOMPRESS, KID_COMPRESS, KID_FROM_UNIFORM, KID_MSM_COUNT, KID_MSM_SCAN, KID_MSM_SCATTER, KID_MSM_ACCUMULATE, KID_MSM_ACC_HEAVY, KID_MSM_REDUCE,
+enum KernelId { KID_DECOMPRESS, KID_COMPRESS, KID_FROM_UNIFORM, KID_MSM_COUNT, KID_MSM_SCAN, KID_MSM_SCATTER, KID_MSM_ACCUMULATE, KID_MSM_REDUCE,
                 KID_MSM_COMBINE, KID_RP_TRANSCRIPT, KID_RP_HEAD, KID_RP_SCALARS, KID_RP_DECOMPRESS, KID_RP_STATIC_REDUCE, KID_IPP_FOLD, KID_SMALL, KID_COUNT };
-const char *const KERNEL_NAMES[KID_COUNT] = {"k_decompress", "k_compress", "k_from_uniform", "k_msm_count", "k_msm_scan", "k_msm_scatter", "k_msm_accumulate", "k_msm_accumulate_heavy",
+const char *const KERNEL_NAMES[KID_COUNT] = {"k_decompress", "k_compress", "k_from_uniform", "k_msm_count", "k_msm_scan", "k_msm_scatter", "k_msm_accumulate",
                                              "k_msm_reduce", "k_msm_combine", "k_rp_transcript", "k_rp_head", "k_rp_scalars", "k_rp_decompress", "k_rp_static_reduce", "k_ipp_fold", "small_kernels"};
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
@@ -58,7 +58,7 @@ struct bp_ctx {
     // regrow -- i.e. move -- a buffer whose address is baked into the captured graph.
     MsmArena ar_rp;
     DevBuf rp_niels, rp_results;
-    DevBuf rp_chal, rp_raw, rp_work, rp_tabs, pow2_tab, rp_proofs, rp_commit, rp_par, rp_contrib, rp_scalars, rp_status, rp_decbad, rp_pidx, rp_offsets, rp_verdict, rp_batch_ok, rp_combined;
+    DevBuf rp_chal, rp_raw, rp_work, rp_tabs, pow2_tab, rp_proofs, rp_commit, rp_par, rp_contrib, rp_part, rp_scalars, rp_status, rp_decbad, rp_pidx, rp_offsets, rp_verdict, rp_batch_ok, rp_combined;
     DevBuf fb_scalars, fb_pidx, fb_offsets;
     uint32_t *h_verdict = nullptr; size_t h_verdict_cap = 0;       // pinned
     uint32_t *h_flag = nullptr;                                      // pinned: combined_ok[BP_MAX_GROUP_BATCHES] | batch_ok[BP_MAX_GROUP_BATCHES]
@@ -154,12 +154,12 @@ int msm_launch(bp_ctx *ctx, MsmArena &ar, const MsmArgs &a, const MsmPlan &p, ge
     // one extra addition per bucket (config 2: 108 -> 71 us alone, same throughput with 24 batches in flight; profiles/r1_timeline.md)
     size_t avg = ((size_t)a.T + a.n_msm - 1) / a.n_msm;
     const int acc_split = avg / nb >= 8 && n_buckets < 65536 ? 2 : 1;
-#define ACC_LAUNCH(SP) LAUNCH(ctx, KID_MSM_ACCUMULATE, k_msm_accumulate<SP><<<blocks_for(n_buckets * SP, 128), 128, 0, s>>>(ar.starts.as<uint32_t>(), ar.cursor.as<uint32_t>(), ar.sorted.as<uint32_t>(), \
-        a.d_offsets, ar.order.as<uint32_t>(), W, nb, n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ar.buckets.as<ge_ext>(), heavy_min))
+    const unsigned heavy_blocks = (unsigned)std::min<size_t>(p.heavy_cap, 148);
+#define ACC_LAUNCH(SP) do { unsigned light_ = blocks_for(n_buckets * SP, MSM_ACC_THREADS); \
+        LAUNCH(ctx, KID_MSM_ACCUMULATE, k_msm_accumulate<SP><<<light_ + heavy_blocks, MSM_ACC_THREADS, 0, s>>>(ar.starts.as<uint32_t>(), ar.cursor.as<uint32_t>(), ar.sorted.as<uint32_t>(), \
+        a.d_offsets, ar.order.as<uint32_t>(), W, nb, n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ar.buckets.as<ge_ext>(), heavy_min, light_, heavy_n, heavy)); } while (0)
     if (acc_split == 2) ACC_LAUNCH(2); else ACC_LAUNCH(1);
 #undef ACC_LAUNCH
-    LAUNCH(ctx, KID_MSM_ACC_HEAVY, k_msm_accumulate_heavy<<<(unsigned)std::min<size_t>(p.heavy_cap, 148), MSM_HEAVY_THREADS, 0, s>>>(ar.starts.as<uint32_t>(), ar.cursor.as<uint32_t>(), ar.sorted.as<uint32_t>(),
-                                                                a.d_offsets, heavy_n, heavy, W, nb, a.d_point_idx, a.d_static, a.d_dynamic, ar.buckets.as<ge_ext>()));
     unsigned rthreads = nb >= 64 ? 64 : 32;      // two warps per segment: fewer scan/tree additions per useful bucket addition
     LAUNCH(ctx, KID_MSM_REDUCE, k_msm_reduce<<<(unsigned)segs, rthreads, 0, s>>>(ar.buckets.as<ge_ext>(), nb, ar.wsums.as<ge_ext>()));
     if (a.n_msm <= 256)      // few MSMs: the Horner chain is pure latency -> four cooperating lanes per MSM
@@ -203,6 +203,32 @@ __global__ void k_rp_point_idx(rp_geom g, uint32_t gens_cap, uint32_t gens_parti
     else v = BP_POINT_DYNAMIC | dyn;
     out[i] = v;
 }
+// decompress to the four extended coordinates (X, Y, Z = 1, T), 4 x 32 canonical bytes per point: the in-memory RistrettoPoint
+// a host caller keeps (bp_decompress_batch / bp_compress_batch)
+__global__ void __launch_bounds__(128) k_decompress_xyzt(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, uint8_t *__restrict__ ok) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint8_t s[32]; ld32(s, in + 32 * i);
+    fe x, y; bool valid = ge_decode(x, y, s);
+    if (!valid) { x = fe_zero(); y = fe_one(); }
+    uint8_t b[32];
+    fe_tobytes(b, x); st32(out + 128 * i, b); fe_tobytes(b, y); st32(out + 128 * i + 32, b);
+    fe_tobytes(b, fe_one()); st32(out + 128 * i + 64, b); fe_tobytes(b, fe_mul(x, y)); st32(out + 128 * i + 96, b);
+    ok[i] = valid ? 1 : 0;
+}
+__global__ void __launch_bounds__(128) k_compress_xyzt(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    ge_ext p; uint8_t b[32];
+    ld32(b, in + 128 * i); p.X = fe_frombytes_raw(b); ld32(b, in + 128 * i + 32); p.Y = fe_frombytes_raw(b);
+    ld32(b, in + 128 * i + 64); p.Z = fe_frombytes_raw(b); ld32(b, in + 128 * i + 96); p.T = fe_frombytes_raw(b);
+    uint8_t s[32]; ge_encode(s, p); st32(out + 32 * i, s);
+}
+// term -> point map of n_msm equal-length MSMs over the same resident point set: term t uses point t mod len
+__global__ void k_iota_mod(uint32_t T, uint32_t len, uint32_t *out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) out[t] = t % len;
+}
 __global__ void k_fill_offsets(uint32_t n, uint32_t stride, uint32_t *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i <= n) out[i] = i * stride;
@@ -241,7 +267,7 @@ void bp_ctx_destroy(bp_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->aux) cudaStreamSynchronize(c->aux);
     if (c->graph) cudaGraphExecDestroy(c->graph);
-    DevBuf *bufs[] = {&c->in_scalars, &c->in_points, &c->in_offsets, &c->niels, &c->ok, &c->msm_err, &c->results, &c->outs, &c->flags, &c->ix_pidx, &c->rp_niels, &c->rp_results, &c->rp_chal, &c->rp_raw, &c->rp_work, &c->rp_tabs, &c->pow2_tab, &c->rp_proofs, &c->rp_commit, &c->rp_par, &c->rp_contrib, &c->rp_scalars,
+    DevBuf *bufs[] = {&c->in_scalars, &c->in_points, &c->in_offsets, &c->niels, &c->ok, &c->msm_err, &c->results, &c->outs, &c->flags, &c->ix_pidx, &c->rp_niels, &c->rp_results, &c->rp_chal, &c->rp_raw, &c->rp_work, &c->rp_tabs, &c->pow2_tab, &c->rp_proofs, &c->rp_commit, &c->rp_par, &c->rp_contrib, &c->rp_part, &c->rp_scalars,
                       &c->rp_status, &c->rp_decbad, &c->rp_pidx, &c->rp_offsets, &c->rp_verdict, &c->rp_batch_ok, &c->rp_combined, &c->fb_scalars, &c->fb_pidx, &c->fb_offsets};
     for (DevBuf *b : bufs) b->release();
     for (MsmArena *ar : {&c->ar_gen, &c->ar_rp}) for (DevBuf *b : {&ar->counts, &ar->starts, &ar->cursor, &ar->order, &ar->sorted, &ar->buckets, &ar->wsums}) b->release();
@@ -339,6 +365,111 @@ int bp_msm(bp_ctx *c, const uint8_t *scalars, const uint8_t *points, size_t n, u
     return rc ? rc : st;
 }
 
+// ---------------------------------------------------------------------------------------------- point values across the boundary
+int bp_decompress_batch(bp_ctx *c, const uint8_t *points, size_t n, uint8_t *xyzt_out, uint8_t *ok) {
+    if (!c || !points || !xyzt_out || !ok) return BP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return BP_OK;
+    BUSY_CHECK(c);
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->in_points.ensure(n * 32)); CK(c, c->outs.ensure(n * 128)); CK(c, c->ok.ensure(n));
+    CK(c, cudaMemcpyAsync(c->in_points.p, points, n * 32, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress_xyzt<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, c->outs.as<uint8_t>(), c->ok.as<uint8_t>()));
+    CK(c, cudaMemcpyAsync(xyzt_out, c->outs.p, n * 128, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(ok, c->ok.p, n, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return BP_OK;
+}
+int bp_compress_batch(bp_ctx *c, const uint8_t *xyzt, size_t n, uint8_t *points_out) {
+    if (!c || !xyzt || !points_out) return BP_ERR_INVALID_ARGUMENT;
+    if (n == 0) return BP_OK;
+    BUSY_CHECK(c);
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->in_points.ensure(n * 128)); CK(c, c->outs.ensure(n * 32));
+    CK(c, cudaMemcpyAsync(c->in_points.p, xyzt, n * 128, cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, KID_COMPRESS, k_compress_xyzt<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, c->outs.as<uint8_t>()));
+    CK(c, cudaMemcpyAsync(points_out, c->outs.p, n * 32, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return BP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- resident point sets (decompressed once, reused by many MSMs)
+}  // extern "C"
+struct bp_points { bp_ctx *ctx = nullptr; size_t n = 0; ge_niels *d_pts = nullptr; uint32_t *d_idx = nullptr; size_t idx_T = 0, idx_len = 0; };
+extern "C" {
+static int points_from_device(bp_ctx *c, const uint8_t *d_compressed, size_t n, bp_points **out) {
+    bp_points *h = new bp_points(); h->ctx = c; h->n = n;
+    cudaError_t e = cudaMalloc((void **)&h->d_pts, n * sizeof(ge_niels));
+    if (e != cudaSuccess) { c->err = std::string("cudaMalloc(points): ") + cudaGetErrorString(e); delete h; return BP_ERR_CUDA; }
+    CK(c, c->ok.ensure(n + 4));
+    uint32_t *d_bad = reinterpret_cast<uint32_t *>(c->ok.as<uint8_t>() + ((n + 3) & ~(size_t)3));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n, 128), 128, 0, c->stream>>>(d_compressed, n, h->d_pts, c->ok.as<uint8_t>()));
+    std::vector<uint8_t> ok(n);
+    CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, n, cudaMemcpyDeviceToHost, c->stream)); CK(c, cudaStreamSynchronize(c->stream));
+    (void)d_bad;
+    for (uint8_t v : ok) if (!v) { cudaFree(h->d_pts); delete h; return BP_ERR_INVALID_POINT; }
+    *out = h; return BP_OK;
+}
+int bp_points_create(bp_ctx *c, const uint8_t *points, size_t n, bp_points **out) {
+    if (!c || !points || !out || n == 0 || n >= (1u << 31)) return BP_ERR_INVALID_ARGUMENT;
+    BUSY_CHECK(c);
+    CK(c, cudaSetDevice(c->device));
+    CK(c, c->in_points.ensure(n * 32));
+    CK(c, cudaMemcpyAsync(c->in_points.p, points, n * 32, cudaMemcpyHostToDevice, c->stream));
+    return points_from_device(c, c->in_points.as<uint8_t>(), n, out);
+}
+int bp_points_create_device(bp_ctx *c, const void *d_points, size_t n, bp_points **out) {
+    if (!c || !d_points || !out || n == 0 || n >= (1u << 31)) return BP_ERR_INVALID_ARGUMENT;
+    BUSY_CHECK(c);
+    CK(c, cudaSetDevice(c->device));
+    return points_from_device(c, (const uint8_t *)d_points, n, out);
+}
+void bp_points_destroy(bp_points *h) { if (!h) return; cudaSetDevice(h->ctx->device); cudaStreamSynchronize(h->ctx->stream); cudaFree(h->d_pts); if (h->d_idx) cudaFree(h->d_idx); delete h; }
+size_t bp_points_count(const bp_points *h) { return h ? h->n : 0; }
+
+// n_msm MSMs of `terms` terms each over the first `terms` points of the set (MSM j uses scalars[j*terms .. (j+1)*terms)); device pointers,
+// nothing synchronised.  No decompression on this path: 32 B of scalar per term is all that is read from the caller.
+int bp_msm_points_device(bp_ctx *c, bp_points *h, const void *d_scalars, size_t n_msm, size_t terms, void *d_outs, void *d_status) {
+    if (!c || !h || !d_scalars || !d_outs || n_msm == 0 || terms == 0 || terms > h->n || n_msm * terms >= (1u << 31)) return BP_ERR_INVALID_ARGUMENT;
+    BUSY_CHECK(c);
+    CK(c, cudaSetDevice(c->device));
+    uint32_t T = (uint32_t)(n_msm * terms), M = (uint32_t)n_msm;
+    cudaStream_t s = c->stream;
+    if (h->idx_T < T || h->idx_len != terms) {
+        CK(c, cudaStreamSynchronize(s));
+        if (h->d_idx) cudaFree(h->d_idx);
+        h->d_idx = nullptr; h->idx_T = 0;
+        CK(c, cudaMalloc((void **)&h->d_idx, (size_t)T * 4));
+        LAUNCH(c, KID_SMALL, k_iota_mod<<<blocks_for(T, 256), 256, 0, s>>>(T, (uint32_t)terms, h->d_idx));
+        h->idx_T = T; h->idx_len = terms;
+    }
+    CK(c, c->in_offsets.ensure(((size_t)M + 1) * 4)); CK(c, c->msm_err.ensure((size_t)M * 4)); CK(c, c->results.ensure((size_t)M * sizeof(ge_ext)));
+    LAUNCH(c, KID_SMALL, k_fill_offsets<<<blocks_for((size_t)M + 1, 256), 256, 0, s>>>(M, (uint32_t)terms, c->in_offsets.as<uint32_t>()));
+    CK(c, cudaMemsetAsync(c->msm_err.p, 0, (size_t)M * 4, s));
+    MsmArgs a{(const uint8_t *)d_scalars, c->in_offsets.as<uint32_t>(), M, T, h->d_idx, h->d_pts, nullptr, c->msm_err.as<uint32_t>(), 0};
+    int rc = msm_core(c, a, c->results.as<ge_ext>());
+    if (rc) return rc;
+    LAUNCH(c, KID_COMPRESS, k_compress<<<blocks_for(M, 128), 128, 0, s>>>(c->results.as<ge_ext>(), M, (uint8_t *)d_outs));
+    if (d_status) { LAUNCH(c, KID_SMALL, k_msm_status<<<blocks_for(M, 128), 128, 0, s>>>(c->msm_err.as<uint32_t>(), M, (uint8_t *)d_status)); }
+    return BP_OK;
+}
+// host-buffer form (pinned memory recommended): H2D of the scalars, the MSMs, D2H of the 32-byte results; synchronises
+int bp_msm_points(bp_ctx *c, bp_points *h, const uint8_t *scalars, size_t n_msm, size_t terms, uint8_t *outs, uint8_t *status) {
+    if (!c || !h || !scalars || !outs || n_msm == 0 || terms == 0) return BP_ERR_INVALID_ARGUMENT;
+    BUSY_CHECK(c);
+    CK(c, cudaSetDevice(c->device));
+    size_t T = n_msm * terms;
+    CK(c, c->in_scalars.ensure(T * 32)); CK(c, c->outs.ensure(n_msm * 32)); CK(c, c->flags.ensure(n_msm));
+    CK(c, cudaMemcpyAsync(c->in_scalars.p, scalars, T * 32, cudaMemcpyHostToDevice, c->stream));
+    int rc = bp_msm_points_device(c, h, c->in_scalars.p, n_msm, terms, c->outs.p, c->flags.p);
+    if (rc) return rc;
+    std::vector<uint8_t> st(n_msm);
+    CK(c, cudaMemcpyAsync(outs, c->outs.p, n_msm * 32, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaMemcpyAsync(st.data(), c->flags.p, n_msm, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (status) memcpy(status, st.data(), n_msm);
+    return BP_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- generators
 static int gens_alloc(bp_ctx *c, size_t cap, size_t parties, bp_gens **out) {
     if (!c || !out || cap == 0 || parties == 0) return BP_ERR_INVALID_ARGUMENT;
@@ -425,6 +556,7 @@ static int rp_ensure(bp_ctx *c, const rp_geom &g) {
     size_t total = (size_t)g.count * g.nbatch, TT = (size_t)g.T * g.nbatch;
     CK(c, c->rp_par.ensure(sizeof(rp_params)));
     CK(c, c->rp_contrib.ensure(total * g.S * sizeof(sc))); CK(c, c->rp_scalars.ensure(TT * 32));
+    CK(c, c->rp_part.ensure((size_t)g.nbatch * ((g.count + RP_CHUNK - 1) / RP_CHUNK) * g.S * sizeof(sc)));
     CK(c, c->rp_status.ensure(total * 4)); CK(c, c->rp_decbad.ensure(total * 4)); CK(c, c->rp_niels.ensure(total * g.D * sizeof(ge_niels)));
     CK(c, c->rp_pidx.ensure(TT * 4)); CK(c, c->rp_offsets.ensure(((size_t)g.nbatch + 1) * 4)); CK(c, c->rp_results.ensure((size_t)g.nbatch * sizeof(ge_ext)));
     CK(c, c->rp_batch_ok.ensure((size_t)g.nbatch * 4)); CK(c, c->rp_combined.ensure((size_t)g.nbatch * 4));
@@ -446,7 +578,7 @@ static int rp_ensure(bp_ctx *c, const rp_geom &g) {
 }
 // signature of every device address the launch sequence of a group bakes into its graph: a regrown (moved) arena invalidates the graph
 static uint64_t rp_ptr_signature(const bp_ctx *c) {
-    const DevBuf *bufs[] = {&c->rp_par, &c->rp_contrib, &c->rp_scalars, &c->rp_status, &c->rp_decbad, &c->rp_niels, &c->rp_pidx, &c->rp_offsets, &c->rp_results, &c->rp_batch_ok, &c->rp_combined,
+    const DevBuf *bufs[] = {&c->rp_par, &c->rp_contrib, &c->rp_part, &c->rp_scalars, &c->rp_status, &c->rp_decbad, &c->rp_niels, &c->rp_pidx, &c->rp_offsets, &c->rp_results, &c->rp_batch_ok, &c->rp_combined,
                             &c->rp_chal, &c->rp_tabs, &c->rp_raw, &c->rp_work, &c->pow2_tab, &c->ar_rp.counts, &c->ar_rp.starts, &c->ar_rp.cursor, &c->ar_rp.order, &c->ar_rp.sorted, &c->ar_rp.buckets, &c->ar_rp.wsums};
     uint64_t h = 1469598103934665603ULL;
     for (const DevBuf *b : bufs) { h ^= (uint64_t)(uintptr_t)b->p; h *= 1099511628211ULL; }
@@ -498,12 +630,13 @@ static int rp_chain(bp_ctx *c, bp_gens *gens, const rp_geom &g) {
     }
     if (s2 != s) CK(c, cudaEventRecord(c->ev_join, s2));
     LAUNCH(c, KID_RP_TRANSCRIPT, k_rp_transcript<<<blocks_for(total, RP_TR_THREADS), RP_TR_THREADS, 0, s>>>(par, g, total, c->rp_raw.as<uint8_t>(), c->rp_status.as<uint32_t>()));
-    LAUNCH(c, KID_RP_HEAD, k_rp_head<<<blocks_for(total, 32), 32 * RP_HEAD_WARPS, 0, s>>>(par, g, c->rp_raw.as<uint8_t>(), total, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(),
-                                                                                          c->pow2_tab.as<sc>(), c->rp_work.as<rp_work>(), c->rp_status.as<uint32_t>()));
+    LAUNCH(c, KID_RP_HEAD, k_rp_head_seq<<<blocks_for(total, 32), 32, 0, s>>>(par, g, c->rp_raw.as<uint8_t>(), total, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(),
+                                                                                  c->pow2_tab.as<sc>(), c->rp_status.as<uint32_t>()));
     if (s2 != s) CK(c, cudaStreamWaitEvent(s, c->ev_join, 0));
-    LAUNCH(c, KID_RP_SCALARS, k_rp_scalars<<<blocks_for((size_t)total * (g.N + g.D), 128), 128, 0, s>>>(g, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(), c->rp_decbad.as<uint32_t>(), total,
-                                                                                                        c->rp_contrib.as<sc>(), d_scal));
-    LAUNCH(c, KID_RP_STATIC_REDUCE, k_rp_static_reduce<<<dim3(g.S, g.nbatch), 128, 0, s>>>(c->rp_contrib.as<sc>(), g, d_scal));
+    const uint32_t nchunks = (g.count + RP_CHUNK - 1) / RP_CHUNK;
+    LAUNCH(c, KID_RP_SCALARS, k_rp_scalars_sum<<<g.nbatch * nchunks, (unsigned)std::min<uint32_t>(128, std::max<uint32_t>(32, g.N)), 0, s>>>(g, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(),
+                                                                                  c->rp_decbad.as<uint32_t>(), c->rp_part.as<sc>(), d_scal));
+    LAUNCH(c, KID_RP_STATIC_REDUCE, k_rp_static_sum<<<dim3(g.S, g.nbatch), 32, 0, s>>>(c->rp_part.as<sc>(), g, d_scal));
     MsmArgs a{d_scal, c->rp_offsets.as<uint32_t>(), g.nbatch, g.T * g.nbatch, c->rp_pidx.as<uint32_t>(), gens->d_table, c->rp_niels.as<ge_niels>(), nullptr, 0};
     int rc = msm_launch(c, c->ar_rp, a, msm_make_plan(a.T, a.n_msm, 0), c->rp_results.as<ge_ext>());
     if (rc) return rc;
@@ -529,14 +662,15 @@ static int rp_verify_queue(bp_ctx *c, bp_gens *gens, const rp_geom &g, const uin
     return rp_chain(c, gens, g);
 }
 
-// per-proof re-check of one batch after its combined check failed: count independent MSMs of S + D terms
-static int rp_verify_fallback(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t batch, uint32_t *d_verdict) {
+// per-proof re-check of the proofs [p0, p0 + count) of a group: count independent MSMs of S + D terms
+static int rp_fallback_range(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t p0, uint32_t count, uint32_t *d_verdict) {
     cudaStream_t s = c->stream;
-    uint32_t count = g.count, row = g.S + g.D, p0 = batch * count; size_t T = (size_t)count * row;
+    uint32_t row = g.S + g.D; size_t T = (size_t)count * row;
     if (T >= (1u << 31)) { c->err = "fallback batch too large"; return BP_ERR_INVALID_ARGUMENT; }
     CK(c, c->fb_scalars.ensure(T * 32)); CK(c, c->fb_pidx.ensure(T * 4)); CK(c, c->fb_offsets.ensure(((size_t)count + 1) * 4));
-    CK(c, c->results.ensure((size_t)std::max(count, g.nbatch) * sizeof(ge_ext)));
-    const uint8_t *dyn = c->rp_scalars.as<uint8_t>() + ((size_t)batch * g.T + g.S) * 32;
+    CK(c, c->results.ensure((size_t)count * sizeof(ge_ext)));
+    uint32_t batch = p0 / g.count, q0 = p0 % g.count;
+    const uint8_t *dyn = c->rp_scalars.as<uint8_t>() + ((size_t)batch * g.T + g.S + (size_t)q0 * g.D) * 32;
     LAUNCH(c, KID_SMALL, k_rp_expand_scalars<<<blocks_for(T, 128), 128, 0, s>>>(c->rp_contrib.as<sc>() + (size_t)p0 * g.S, dyn, g, count, c->fb_scalars.as<uint8_t>()));
     LAUNCH(c, KID_SMALL, k_rp_point_idx<<<blocks_for(T, 256), 256, 0, s>>>(g, (uint32_t)gens->cap, (uint32_t)gens->parties, count, 1, p0 * g.D, c->fb_pidx.as<uint32_t>()));
     LAUNCH(c, KID_SMALL, k_fill_offsets<<<blocks_for((size_t)count + 1, 256), 256, 0, s>>>(count, row, c->fb_offsets.as<uint32_t>()));
@@ -546,7 +680,39 @@ static int rp_verify_fallback(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32
     LAUNCH(c, KID_SMALL, k_rp_verdict_proofs<<<blocks_for(count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>() + p0, c->rp_decbad.as<uint32_t>() + p0, c->results.as<ge_ext>(), count, d_verdict + p0));
     return BP_OK;
 }
-
+// A batch whose combined check failed.  Level 1: one combined MSM per chunk of RP_CHUNK proofs, from the partial sums the main path
+// already holds (one pipeline pass over the batch's ~T terms).  Level 2: the proofs of the failing chunks, each with its own MSM
+// (mod.rs:421-447 per proof).  One bad proof in 1024 costs two small passes instead of 1024 147-term MSMs.
+static int rp_verify_fallback(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32_t batch, uint32_t *d_verdict, bool *contrib_ready) {
+    cudaStream_t s = c->stream;
+    const uint32_t nch = (g.count + RP_CHUNK - 1) / RP_CHUNK, row = g.S + RP_CHUNK * g.D, p0 = batch * g.count;
+    size_t T = (size_t)nch * row;
+    if (T >= (1u << 31)) { c->err = "fallback batch too large"; return BP_ERR_INVALID_ARGUMENT; }
+    CK(c, c->fb_scalars.ensure(T * 32)); CK(c, c->fb_pidx.ensure(T * 4)); CK(c, c->fb_offsets.ensure(((size_t)nch + 1) * 4));
+    CK(c, c->results.ensure((size_t)nch * sizeof(ge_ext))); CK(c, c->flags.ensure((size_t)nch * 4));
+    LAUNCH(c, KID_SMALL, k_rp_chunk_rows<<<blocks_for(T, 128), 128, 0, s>>>(c->rp_part.as<sc>() + (size_t)batch * nch * g.S, c->rp_scalars.as<uint8_t>() + ((size_t)batch * g.T + g.S) * 32, g,
+                                                                              (uint32_t)gens->cap, (uint32_t)gens->parties, p0 * g.D, c->fb_scalars.as<uint8_t>(), c->fb_pidx.as<uint32_t>()));
+    LAUNCH(c, KID_SMALL, k_fill_offsets<<<blocks_for((size_t)nch + 1, 256), 256, 0, s>>>(nch, row, c->fb_offsets.as<uint32_t>()));
+    MsmArgs a{c->fb_scalars.as<uint8_t>(), c->fb_offsets.as<uint32_t>(), nch, (uint32_t)T, c->fb_pidx.as<uint32_t>(), gens->d_table, c->rp_niels.as<ge_niels>(), nullptr, 0};
+    int rc = msm_core(c, a, c->results.as<ge_ext>());
+    if (rc) return rc;
+    LAUNCH(c, KID_SMALL, k_rp_verdict_chunks<<<blocks_for(g.count, 128), 128, 0, s>>>(c->rp_status.as<uint32_t>() + p0, c->rp_decbad.as<uint32_t>() + p0, c->results.as<ge_ext>(), g.count,
+                                                                                      d_verdict + p0, c->flags.as<uint32_t>()));
+    std::vector<uint32_t> ok(nch);
+    CK(c, cudaMemcpyAsync(ok.data(), c->flags.p, (size_t)nch * 4, cudaMemcpyDeviceToHost, s)); CK(c, cudaStreamSynchronize(s));
+    uint32_t nfail = 0; for (uint32_t v : ok) nfail += v ? 0 : 1;
+    if (nfail == 0) return BP_OK;       // cannot happen when the batch's combination failed, short of a 2^-128 cancellation between chunk weights
+    if (!*contrib_ready) {   // the combined path keeps only sums: the per-proof static-term scalars are produced here, on the reject path (whole group; idempotent)
+        const uint32_t total = g.count * g.nbatch;
+        LAUNCH(c, KID_RP_SCALARS, k_rp_scalars<<<blocks_for((size_t)total * (g.N + g.D), 128), 128, 0, s>>>(g, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(), c->rp_decbad.as<uint32_t>(), total,
+                                                                                                            c->rp_contrib.as<sc>(), c->rp_scalars.as<uint8_t>()));
+        *contrib_ready = true;
+    }
+    if (nfail > 4) return rp_fallback_range(c, gens, g, p0, g.count, d_verdict);      // many bad chunks: one pass over the whole batch
+    for (uint32_t ch = 0; ch < nch; ch++)
+        if (!ok[ch]) { rc = rp_fallback_range(c, gens, g, p0 + ch * RP_CHUNK, std::min<uint32_t>(RP_CHUNK, g.count - ch * RP_CHUNK), d_verdict); if (rc) return rc; }
+    return BP_OK;
+}
 
 int bp_rangeproof_verify_reserve(bp_ctx *c, bp_gens *gens, size_t n, size_t m, size_t count, size_t n_batches) {
     if (!c || !gens) return BP_ERR_INVALID_ARGUMENT;
@@ -615,10 +781,10 @@ int bp_rangeproof_verify_group_finish(bp_ctx *c, uint8_t *verdicts, uint8_t *bat
     if (vs.param_verdict != BP_PROOF_OK) { memset(verdicts, (int)vs.param_verdict, vs.total); if (batch_ok) memset(batch_ok, 0, 1); return BP_OK; }
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
-    bool redo = false;
+    bool redo = false, contrib_ready = false;
     for (uint32_t b = 0; b < vs.g.nbatch; b++)
-        if (c->h_flag[b] == 0) {            // this batch's combined check failed: find the offenders proof by proof
-            int rc = rp_verify_fallback(c, vs.gens, vs.g, b, c->rp_verdict.as<uint32_t>());
+        if (c->h_flag[b] == 0) {            // this batch's combined check failed: find the offenders (chunks of 32, then proof by proof)
+            int rc = rp_verify_fallback(c, vs.gens, vs.g, b, c->rp_verdict.as<uint32_t>(), &contrib_ready);
             if (rc) return rc;
             redo = true;
         }
@@ -818,6 +984,132 @@ int bp_ipp_fold(bp_ipp *s, size_t n_half, const uint8_t *g_lo, const uint8_t *g_
     LAUNCH(c, KID_IPP_FOLD, k_ipp_fold<<<blocks_for(h, 64), 64, 0, st>>>(s->pts, (uint32_t)h, d, d + cnt * 32, stride));
     LAUNCH(c, KID_IPP_FOLD, k_ipp_fold<<<blocks_for(h, 64), 64, 0, st>>>(s->pts + s->N, (uint32_t)h, d + 2 * cnt * 32, d + 3 * cnt * 32, stride));
     CK(c, cudaStreamSynchronize(st));          // the scalar staging buffer is reused by the next round
+    return BP_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- inner-product prover, device-resident state
+}  // extern "C"
+struct bp_ippx {
+    bp_ctx *ctx = nullptr; uint32_t N = 0, B = 0, n = 0;
+    const ge_niels *d_static = nullptr; ge_niels *own_pts = nullptr;      // the gens table, or the session's own [G (N) | H (N)]
+    ge_niels *d_q = nullptr;                                               // B points Q
+    DevBuf a, b, cG, cH, gidx, hidx, scal, pidx, offs, in, outs;
+};
+extern "C" {
+static int ippx_alloc(bp_ctx *c, size_t N, size_t B, bp_ippx **out) {
+    if (!c || !out || N == 0 || (N & (N - 1)) || B == 0 || 2 * B * (N + 1) >= (1u << 31)) return BP_ERR_INVALID_ARGUMENT;      // power of two (inner_product_proof.rs:67)
+    BUSY_CHECK(c);
+    CK(c, cudaSetDevice(c->device));
+    bp_ippx *s = new bp_ippx(); s->ctx = c; s->N = (uint32_t)N; s->B = (uint32_t)B; s->n = (uint32_t)N;
+    size_t BN = B * N;
+    cudaError_t e = cudaMalloc((void **)&s->d_q, B * sizeof(ge_niels));
+    if (e != cudaSuccess) { c->err = std::string("cudaMalloc(ippx): ") + cudaGetErrorString(e); delete s; return BP_ERR_CUDA; }
+    for (DevBuf *b : {&s->a, &s->b, &s->cG, &s->cH}) CK(c, b->ensure(BN * sizeof(sc)));
+    CK(c, s->gidx.ensure(N * 4)); CK(c, s->hidx.ensure(N * 4)); CK(c, s->scal.ensure(2 * B * (N + 1) * 32)); CK(c, s->pidx.ensure(2 * B * (N + 1) * 4));
+    CK(c, s->offs.ensure((2 * B + 1) * 4)); CK(c, s->in.ensure(std::max<size_t>(4 * BN * 32, 64 * B))); CK(c, s->outs.ensure(64 * B));
+    *out = s; return BP_OK;
+}
+static void ippx_free(bp_ippx *s) {
+    cudaFree(s->d_q); if (s->own_pts) cudaFree(s->own_pts);
+    for (DevBuf *b : {&s->a, &s->b, &s->cG, &s->cH, &s->gidx, &s->hidx, &s->scal, &s->pidx, &s->offs, &s->in, &s->outs}) b->release();
+    delete s;
+}
+// common tail of the two begin forms: Q points, scalar vectors (B x N canonical scalars each; Gf / Hf may be NULL = all ones)
+static int ippx_load(bp_ippx *s, const uint8_t *Q, const uint8_t *Gf, const uint8_t *Hf, const uint8_t *a, const uint8_t *b) {
+    bp_ctx *c = s->ctx; cudaStream_t st = c->stream; size_t BN = (size_t)s->B * s->N;
+    for (const uint8_t *v : {a, b}) if (check_scalars_canonical(v, BN)) return BP_ERR_NONCANONICAL_SCALAR;
+    for (const uint8_t *v : {Gf, Hf}) if (v && check_scalars_canonical(v, BN)) return BP_ERR_NONCANONICAL_SCALAR;
+    uint8_t *din = s->in.as<uint8_t>();
+    CK(c, cudaMemcpyAsync(din, a, BN * 32, cudaMemcpyHostToDevice, st)); CK(c, cudaMemcpyAsync(din + BN * 32, b, BN * 32, cudaMemcpyHostToDevice, st));
+    if (Gf) CK(c, cudaMemcpyAsync(din + 2 * BN * 32, Gf, BN * 32, cudaMemcpyHostToDevice, st));
+    if (Hf) CK(c, cudaMemcpyAsync(din + 3 * BN * 32, Hf, BN * 32, cudaMemcpyHostToDevice, st));
+    ippx_geom g{s->N, s->B, s->n};
+    LAUNCH(c, KID_SMALL, k_ippx_init<<<blocks_for(BN, 128), 128, 0, st>>>(g, din, din + BN * 32, Gf ? din + 2 * BN * 32 : nullptr, Hf ? din + 3 * BN * 32 : nullptr,
+                                                                         s->a.as<sc>(), s->b.as<sc>(), s->cG.as<sc>(), s->cH.as<sc>()));
+    CK(c, c->in_points.ensure((size_t)s->B * 32)); CK(c, c->ok.ensure(s->B));
+    CK(c, cudaMemcpyAsync(c->in_points.p, Q, (size_t)s->B * 32, cudaMemcpyHostToDevice, st));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(s->B, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), s->B, s->d_q, c->ok.as<uint8_t>()));
+    std::vector<uint8_t> ok(s->B);
+    CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, s->B, cudaMemcpyDeviceToHost, st)); CK(c, cudaStreamSynchronize(st));
+    for (uint8_t v : ok) if (!v) return BP_ERR_INVALID_POINT;
+    LAUNCH(c, KID_SMALL, k_fill_offsets<<<blocks_for((size_t)2 * s->B + 1, 256), 256, 0, st>>>(2 * s->B, s->N + 1, s->offs.as<uint32_t>()));
+    return BP_OK;
+}
+int bp_ippx_begin(bp_ctx *c, bp_gens *gens, size_t n, size_t m, size_t n_proofs, const uint8_t *Q, const uint8_t *Gf, const uint8_t *Hf, const uint8_t *a, const uint8_t *b, bp_ippx **out) {
+    if (!gens || !Q || !a || !b || n == 0 || m == 0 || n > gens->cap || m > gens->parties) return BP_ERR_INVALID_ARGUMENT;
+    size_t N = n * m;
+    int rc = ippx_alloc(c, N, n_proofs, out); if (rc) return rc;
+    bp_ippx *s = *out; s->d_static = gens->d_table;
+    std::vector<uint32_t> idx(2 * N);
+    for (size_t q = 0; q < N; q++) {          // BulletproofGens::G(n, m) / H(n, m) iterator order (generators.rs:207-259)
+        idx[q] = (uint32_t)(2 + (q / n) * gens->cap + (q % n));
+        idx[N + q] = (uint32_t)(2 + gens->parties * gens->cap + (q / n) * gens->cap + (q % n));
+    }
+    CK(c, cudaMemcpyAsync(s->gidx.p, idx.data(), N * 4, cudaMemcpyHostToDevice, c->stream)); CK(c, cudaMemcpyAsync(s->hidx.p, idx.data() + N, N * 4, cudaMemcpyHostToDevice, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    rc = ippx_load(s, Q, Gf, Hf, a, b);
+    if (rc) { ippx_free(s); *out = nullptr; }
+    return rc;
+}
+int bp_ippx_begin_points(bp_ctx *c, const uint8_t *G, const uint8_t *H, size_t N, size_t n_proofs, const uint8_t *Q, const uint8_t *Gf, const uint8_t *Hf, const uint8_t *a, const uint8_t *b, bp_ippx **out) {
+    if (!G || !H || !Q || !a || !b) return BP_ERR_INVALID_ARGUMENT;
+    int rc = ippx_alloc(c, N, n_proofs, out); if (rc) return rc;
+    bp_ippx *s = *out; cudaStream_t st = c->stream;
+    cudaError_t e = cudaMalloc((void **)&s->own_pts, 2 * N * sizeof(ge_niels));
+    if (e != cudaSuccess) { c->err = std::string("cudaMalloc(ippx points): ") + cudaGetErrorString(e); ippx_free(s); *out = nullptr; return BP_ERR_CUDA; }
+    s->d_static = s->own_pts;
+    CK(c, c->in_points.ensure(2 * N * 32)); CK(c, c->ok.ensure(2 * N));
+    CK(c, cudaMemcpyAsync(c->in_points.p, G, N * 32, cudaMemcpyHostToDevice, st)); CK(c, cudaMemcpyAsync(c->in_points.as<uint8_t>() + N * 32, H, N * 32, cudaMemcpyHostToDevice, st));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(2 * N, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), 2 * N, s->own_pts, c->ok.as<uint8_t>()));
+    std::vector<uint8_t> ok(2 * N); std::vector<uint32_t> idx(2 * N);
+    for (size_t q = 0; q < 2 * N; q++) idx[q] = (uint32_t)q;
+    CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, 2 * N, cudaMemcpyDeviceToHost, st));
+    CK(c, cudaMemcpyAsync(s->gidx.p, idx.data(), N * 4, cudaMemcpyHostToDevice, st)); CK(c, cudaMemcpyAsync(s->hidx.p, idx.data() + N, N * 4, cudaMemcpyHostToDevice, st));
+    CK(c, cudaStreamSynchronize(st));
+    for (uint8_t v : ok) if (!v) { ippx_free(s); *out = nullptr; return BP_ERR_INVALID_POINT; }
+    rc = ippx_load(s, Q, Gf, Hf, a, b);
+    if (rc) { ippx_free(s); *out = nullptr; }
+    return rc;
+}
+void bp_ippx_end(bp_ippx *s) { if (!s) return; cudaSetDevice(s->ctx->device); cudaStreamSynchronize(s->ctx->stream); ippx_free(s); }
+size_t bp_ippx_current_len(const bp_ippx *s) { return s ? s->n : 0; }
+// L and R of the current round for every proof (inner_product_proof.rs:87-113 / 153-163): LR_out = n_proofs x (L | R) compressed; synchronises
+int bp_ippx_round(bp_ippx *s, uint8_t *LR_out) {
+    if (!s || !LR_out || s->n < 2) return BP_ERR_INVALID_ARGUMENT;
+    bp_ctx *c = s->ctx; BUSY_CHECK(c); CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->stream; ippx_geom g{s->N, s->B, s->n};
+    uint32_t M = 2 * s->B, T = M * (s->N + 1);
+    LAUNCH(c, KID_SMALL, k_ippx_inner<<<M, 128, 0, st>>>(g, s->a.as<sc>(), s->b.as<sc>(), s->scal.as<uint8_t>()));
+    LAUNCH(c, KID_SMALL, k_ippx_rows<<<blocks_for((size_t)s->B * s->N, 128), 128, 0, st>>>(g, s->a.as<sc>(), s->b.as<sc>(), s->cG.as<sc>(), s->cH.as<sc>(), s->gidx.as<uint32_t>(), s->hidx.as<uint32_t>(),
+                                                                                          s->scal.as<uint8_t>(), s->pidx.as<uint32_t>()));
+    CK(c, c->results.ensure((size_t)M * sizeof(ge_ext)));
+    MsmArgs a{s->scal.as<uint8_t>(), s->offs.as<uint32_t>(), M, T, s->pidx.as<uint32_t>(), s->d_static, s->d_q, nullptr, 0};
+    int rc = msm_core(c, a, c->results.as<ge_ext>());
+    if (rc) return rc;
+    LAUNCH(c, KID_COMPRESS, k_compress<<<blocks_for(M, 128), 128, 0, st>>>(c->results.as<ge_ext>(), M, s->outs.as<uint8_t>()));
+    CK(c, cudaMemcpyAsync(LR_out, s->outs.p, (size_t)M * 32, cudaMemcpyDeviceToHost, st)); CK(c, cudaStreamSynchronize(st));
+    return BP_OK;
+}
+// apply the challenges u (and their inverses), one pair per proof; halves the current length
+int bp_ippx_fold(bp_ippx *s, const uint8_t *u, const uint8_t *u_inv) {
+    if (!s || !u || !u_inv || s->n < 2) return BP_ERR_INVALID_ARGUMENT;
+    bp_ctx *c = s->ctx; BUSY_CHECK(c); CK(c, cudaSetDevice(c->device));
+    if (check_scalars_canonical(u, s->B) || check_scalars_canonical(u_inv, s->B)) return BP_ERR_NONCANONICAL_SCALAR;
+    cudaStream_t st = c->stream; ippx_geom g{s->N, s->B, s->n};
+    uint8_t *din = s->in.as<uint8_t>();
+    CK(c, cudaMemcpyAsync(din, u, (size_t)s->B * 32, cudaMemcpyHostToDevice, st)); CK(c, cudaMemcpyAsync(din + (size_t)s->B * 32, u_inv, (size_t)s->B * 32, cudaMemcpyHostToDevice, st));
+    LAUNCH(c, KID_IPP_FOLD, k_ippx_fold<<<blocks_for((size_t)s->B * s->N, 128), 128, 0, st>>>(g, din, din + (size_t)s->B * 32, s->a.as<sc>(), s->b.as<sc>(), s->cG.as<sc>(), s->cH.as<sc>()));
+    CK(c, cudaStreamSynchronize(st));          // the staging buffer is reused by the next call
+    s->n >>= 1;
+    return BP_OK;
+}
+// the final a, b (inner_product_proof.rs:187-192): ab_out = n_proofs x (a | b)
+int bp_ippx_finish(bp_ippx *s, uint8_t *ab_out) {
+    if (!s || !ab_out || s->n != 1) return BP_ERR_INVALID_ARGUMENT;
+    bp_ctx *c = s->ctx; BUSY_CHECK(c); CK(c, cudaSetDevice(c->device));
+    ippx_geom g{s->N, s->B, s->n};
+    LAUNCH(c, KID_SMALL, k_ippx_final<<<blocks_for(s->B, 128), 128, 0, c->stream>>>(g, s->a.as<sc>(), s->b.as<sc>(), s->outs.as<uint8_t>()));
+    CK(c, cudaMemcpyAsync(ab_out, s->outs.p, (size_t)s->B * 64, cudaMemcpyDeviceToHost, c->stream)); CK(c, cudaStreamSynchronize(c->stream));
     return BP_OK;
 }
 

@@ -208,20 +208,29 @@ __global__ void __launch_bounds__(256) k_msm_order(const uint32_t *__restrict__ 
                                                    uint32_t *__restrict__ heavy_n, uint32_t *__restrict__ heavy) {
     __shared__ uint32_t base[MSM_SIZE_BINS];
     __shared__ uint32_t wsum[8];
+    __shared__ uint32_t local[MSM_SIZE_BINS];          // this block's buckets per bin, then the block's base within the bin
     {   // exclusive scan of the 256-bin histogram, redundantly per block
         uint32_t v = size_hist[threadIdx.x], lane = threadIdx.x & 31, wid = threadIdx.x >> 5, x = v;
         for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, x, d); if (lane >= (uint32_t)d) x += o; }
         if (lane == 31) wsum[wid] = x;
+        local[threadIdx.x] = 0;
         __syncthreads();
         uint32_t b = 0; for (uint32_t k = 0; k < wid; k++) b += wsum[k];
         base[threadIdx.x] = b + x - v;
         __syncthreads();
     }
+    // rank within (block, bin) through shared-memory atomics, then ONE global atomic per non-empty bin of the block: the buckets of a
+    // window have nearly equal sizes, so per-bucket global atomics on a handful of bin cursors serialise (46 us for 786k buckets)
     size_t gb = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gb >= n_buckets) return;
-    uint32_t cnt = counts[gb];
+    bool live = gb < n_buckets;
+    uint32_t cnt = live ? counts[gb] : 0;
     uint32_t bin = MSM_SIZE_BINS - 1 - min(cnt, (uint32_t)MSM_SIZE_BINS - 1);
-    order[base[bin] + atomicAdd(bin_cursor + bin, 1u)] = (uint32_t)gb;
+    uint32_t rank = live ? atomicAdd(&local[bin], 1u) : 0;
+    __syncthreads();
+    { uint32_t mine = local[threadIdx.x]; __syncthreads(); local[threadIdx.x] = mine ? atomicAdd(bin_cursor + threadIdx.x, mine) : 0; }
+    __syncthreads();
+    if (!live) return;
+    order[base[bin] + local[bin] + rank] = (uint32_t)gb;
     if (cnt >= heavy_min) heavy[atomicAdd(heavy_n, 1u)] = (uint32_t)gb;
 }
 // pass 3: scatter term ids (sign in bit 31) into their bucket's slice
@@ -247,6 +256,44 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *__restrict__
         sorted[msm_slice_base(o0, len, (uint32_t)w, W) + pos] = t | (d < 0 ? 0x80000000u : 0u);
     }
 }
+// heavy buckets (size >= heavy_min, listed by k_msm_order): one 128-thread block per bucket, grid-stride over the list: threads take
+// strided entries, then a shuffle tree + one shared-memory round add the partial sums.  Runs in the tail blocks of k_msm_accumulate's
+// grid (a separate launch would wait for an SM with a free block slot behind the wide kernels of the other groups in flight).
+#define MSM_ACC_THREADS 128
+__device__ __noinline__ void msm_heavy_role(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
+                                            const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ heavy_n, const uint32_t *__restrict__ heavy, int W, uint32_t nb,
+                                            const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,
+                                            ge_ext *__restrict__ buckets, uint32_t first, uint32_t stride) {
+    __shared__ ge_ext sm[MSM_ACC_THREADS / 32];
+    uint32_t n_heavy = *heavy_n, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (uint32_t h = first; h < n_heavy; h += stride) {
+        size_t gb = heavy[h];
+        size_t seg = gb / nb; uint32_t msm = (uint32_t)(seg / W), w = (uint32_t)(seg % W);
+        uint32_t o0 = __ldg(offsets + msm), len = __ldg(offsets + msm + 1) - o0;
+        const uint32_t *slice = sorted + msm_slice_base(o0, len, w, W);
+        uint32_t lo = starts[gb], hi = ends[gb];
+        ge_ext acc = ge_identity();
+        for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
+            uint32_t v = __ldg(slice + e), t = v & 0x7fffffffu;
+            uint32_t pi = point_idx ? __ldg(point_idx + t) : (t | BP_POINT_DYNAMIC);
+            const ge_niels *src = (pi & BP_POINT_DYNAMIC) ? pts_dynamic + (pi & 0x7fffffffu) : pts_static + pi;
+            ge_niels q = ldg_niels(src);
+            if (v & 0x80000000u) q = ge_niels_neg(q);
+            acc = ge_madd(acc, q);
+        }
+#pragma unroll 1
+        for (int d = 16; d >= 1; d >>= 1) { ge_ext o = shfl_down_ext(acc, d); acc = ge_add(acc, o); }
+        if (lane == 0) sm[wid] = acc;
+        __syncthreads();
+        if (wid == 0) {
+            ge_ext r = lane < (blockDim.x >> 5) ? sm[lane] : ge_identity();
+#pragma unroll 1
+            for (int d = 2; d >= 1; d >>= 1) { ge_ext o = shfl_down_ext(r, d); r = ge_add(r, o); }
+            if (lane == 0) st_ext(buckets + gb, r);
+        }
+        __syncthreads();
+    }
+}
 // pass 4: bucket accumulation, SPLIT adjacent lanes per bucket: each sums every SPLIT-th +-point of the bucket's slice (mixed
 // additions), a shuffle tree adds the partial sums.  SPLIT > 1 trades (SPLIT-1) full additions per bucket for SPLIT x more warps
 // in flight and a SPLIT x shorter serial chain per thread.
@@ -254,7 +301,11 @@ template <int SPLIT>
 __global__ void __launch_bounds__(128, 5) k_msm_accumulate(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
                                                         const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, int W, uint32_t nb, size_t n_buckets,
                                                         const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,
-                                                        ge_ext *__restrict__ buckets, uint32_t heavy_min) {
+                                                        ge_ext *__restrict__ buckets, uint32_t heavy_min, uint32_t n_light_blocks, const uint32_t *__restrict__ heavy_n, const uint32_t *__restrict__ heavy) {
+    if (blockIdx.x >= n_light_blocks) {       // the grid's tail blocks own the heavy buckets (listed by k_msm_order), one block per bucket
+        msm_heavy_role(starts, ends, sorted, offsets, heavy_n, heavy, W, nb, point_idx, pts_static, pts_dynamic, buckets, blockIdx.x - n_light_blocks, gridDim.x - n_light_blocks);
+        return;
+    }
     size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t b = tid / SPLIT; uint32_t sub = (uint32_t)(tid % SPLIT);
     bool live = b < n_buckets;
@@ -280,43 +331,6 @@ __global__ void __launch_bounds__(128, 5) k_msm_accumulate(const uint32_t *__res
         for (int d = SPLIT / 2; d >= 1; d >>= 1) { ge_ext o = shfl_down_ext(acc, d); acc = ge_add(acc, o); }
     }
     if (live && sub == 0) st_ext(buckets + gb, acc);
-}
-// pass 4b: heavy buckets, one block per bucket (grid-stride over the list k_msm_order built): threads take strided
-// entries, then a shuffle tree + one shared-memory round add the partial sums
-#define MSM_HEAVY_THREADS 256      // 256 x 118 registers: two blocks fit beside other kernels' blocks on an SM
-__global__ void __launch_bounds__(MSM_HEAVY_THREADS) k_msm_accumulate_heavy(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
-                                                        const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ heavy_n, const uint32_t *__restrict__ heavy, int W, uint32_t nb,
-                                                        const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,
-                                                        ge_ext *__restrict__ buckets) {
-    __shared__ ge_ext sm[MSM_HEAVY_THREADS / 32];
-    uint32_t n_heavy = *heavy_n, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (uint32_t h = blockIdx.x; h < n_heavy; h += gridDim.x) {
-        size_t gb = heavy[h];
-        size_t seg = gb / nb; uint32_t msm = (uint32_t)(seg / W), w = (uint32_t)(seg % W);
-        uint32_t o0 = __ldg(offsets + msm), len = __ldg(offsets + msm + 1) - o0;
-        const uint32_t *slice = sorted + msm_slice_base(o0, len, w, W);
-        uint32_t lo = starts[gb], hi = ends[gb];
-        ge_ext acc = ge_identity();
-        for (uint32_t e = lo + threadIdx.x; e < hi; e += blockDim.x) {
-            uint32_t v = __ldg(slice + e), t = v & 0x7fffffffu;
-            uint32_t pi = point_idx ? __ldg(point_idx + t) : (t | BP_POINT_DYNAMIC);
-            const ge_niels *src = (pi & BP_POINT_DYNAMIC) ? pts_dynamic + (pi & 0x7fffffffu) : pts_static + pi;
-            ge_niels q = ldg_niels(src);
-            if (v & 0x80000000u) q = ge_niels_neg(q);
-            acc = ge_madd(acc, q);
-        }
-#pragma unroll 1
-        for (int d = 16; d >= 1; d >>= 1) { ge_ext o = shfl_down_ext(acc, d); acc = ge_add(acc, o); }
-        if (lane == 0) sm[wid] = acc;
-        __syncthreads();
-        if (wid == 0) {
-            ge_ext r = lane < (blockDim.x >> 5) ? sm[lane] : ge_identity();
-#pragma unroll 1
-            for (int d = 16; d >= 1; d >>= 1) { ge_ext o = shfl_down_ext(r, d); r = ge_add(r, o); }
-            if (lane == 0) st_ext(buckets + gb, r);
-        }
-        __syncthreads();
-    }
 }
 // pass 5: bucket reduction  R = sum_j (j+1) B_j  per segment, one block per segment.
 // Each thread owns a contiguous chunk; a warp-shuffle suffix scan over the chunk sums gives every
@@ -441,6 +455,86 @@ __global__ void __launch_bounds__(64) k_ipp_fold(ge_niels *__restrict__ P, uint3
     }
     fe zf = fe_invert(acc.Z);
     st_niels(P + i, ge_to_niels_affine(fe_mul(acc.X, zf), fe_mul(acc.Y, zf)));
+}
+// ------------------------------------------------------------------ K4': inner-product prover without generator folding
+// InnerProductProof::create (inner_product_proof.rs:69-185) folds G and H every round (N two-term scalar multiplications in total).
+// The device session never folds points: after rounds with challenges u_1..u_j the folded generator at position i is the combination
+//   G^(j)[i] = sum over original indices idx = i (mod n_j) of cG[idx] G[idx],   cG[idx] = G_factors[idx] * prod_r u_r^(+-1)
+// (sign by the index bit the round consumed; H likewise with the signs swapped), so L_j and R_j are MSMs of N + 1 terms over the
+// ORIGINAL resident points with scalars a_L[pos - h] * cG[idx] etc.; a round costs O(N) scalar products and one MSM launch chain.
+// a, b are kept in Montgomery form, the coefficient vectors cG, cH in plain form, so that every product needed as an MSM scalar comes
+// out of one Montgomery multiplication as a canonical value.  B proofs of the same length run side by side.
+struct ippx_geom { uint32_t N, B, n; };        // N = original length, n = current length (power of two), B proofs
+__global__ void __launch_bounds__(128) k_ippx_init(ippx_geom g, const uint8_t *__restrict__ a_in, const uint8_t *__restrict__ b_in, const uint8_t *__restrict__ Gf, const uint8_t *__restrict__ Hf,
+                                                   sc *__restrict__ a, sc *__restrict__ b, sc *__restrict__ cG, sc *__restrict__ cH) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)g.B * g.N) return;
+    a[i] = sc_to_mont(sc_load(a_in + 32 * i)); b[i] = sc_to_mont(sc_load(b_in + 32 * i));
+    sc one = sc_zero(); one.v[0] = 1;
+    cG[i] = Gf ? sc_load(Gf + 32 * i) : one; cH[i] = Hf ? sc_load(Hf + 32 * i) : one;
+}
+// c_L = <a_L, b_R>, c_R = <a_R, b_L> (inner_product_proof.rs:84-85,150-151): block (proof, which), canonical bytes into slot N of the proof's L / R scalar row
+__global__ void __launch_bounds__(128) k_ippx_inner(ippx_geom g, const sc *__restrict__ a, const sc *__restrict__ b, uint8_t *__restrict__ scal) {
+    __shared__ sc sm[4];
+    const uint32_t p = blockIdx.x >> 1, which = blockIdx.x & 1, h = g.n >> 1;
+    const sc *x = a + (size_t)p * g.N + (which ? h : 0), *y = b + (size_t)p * g.N + (which ? 0 : h);
+    sc acc = sc_zero();
+    for (uint32_t i0 = threadIdx.x * 16; i0 < h; i0 += blockDim.x * 16) {      // 16 products per lazy reduction
+        sc_wide w = sc_wide_zero();
+        for (uint32_t i = i0; i < min(i0 + 16, h); i++) sc_wide_mac(w, x[i], y[i]);
+        acc = sc_add(acc, sc_wide_redc(w));
+    }
+    for (int d = 16; d >= 1; d >>= 1) { sc o; for (int i = 0; i < 8; i++) o.v[i] = __shfl_down_sync(0xffffffffu, acc.v[i], d); acc = sc_add(acc, o); }
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (uint32_t k = 1; k < (blockDim.x >> 5); k++) acc = sc_add(acc, sm[k]);
+        uint8_t bytes[32]; sc_store(bytes, sc_from_mont(acc)); st32(scal + (((size_t)p * 2 + which) * (g.N + 1) + g.N) * 32, bytes);
+    }
+}
+// MSM rows of the round: per proof an L row and an R row of N + 1 (scalar, point index) pairs.  gidx/hidx = table slots of the original G / H
+// points, Q = dynamic point p.
+__global__ void __launch_bounds__(128) k_ippx_rows(ippx_geom g, const sc *__restrict__ a, const sc *__restrict__ b, const sc *__restrict__ cG, const sc *__restrict__ cH,
+                                                   const uint32_t *__restrict__ gidx, const uint32_t *__restrict__ hidx, uint8_t *__restrict__ scal, uint32_t *__restrict__ pidx) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)g.B * g.N) return;
+    const uint32_t p = (uint32_t)(t / g.N), idx = (uint32_t)(t % g.N), h = g.n >> 1, pos = idx & (g.n - 1), blk = idx / g.n;
+    const sc *ap = a + (size_t)p * g.N, *bp_ = b + (size_t)p * g.N;
+    const size_t rowL = ((size_t)p * 2) * (g.N + 1), rowR = rowL + g.N + 1;
+    uint8_t bytes[32];
+    // G[idx]: right half -> L with a_L, left half -> R with a_R (inner_product_proof.rs:87-99,101-113)
+    { bool right = pos >= h; uint32_t i = right ? pos - h : pos;
+      sc v = sc_mont_mul(right ? ap[i] : ap[h + i], cG[t]);
+      size_t slot = (right ? rowL : rowR) + blk * h + i;
+      sc_store(bytes, v); st32(scal + slot * 32, bytes); pidx[slot] = gidx[idx]; }
+    // H[idx]: left half -> L with b_R, right half -> R with b_L
+    { bool left = pos < h; uint32_t i = left ? pos : pos - h;
+      sc v = sc_mont_mul(left ? bp_[h + i] : bp_[i], cH[t]);
+      size_t slot = (left ? rowL : rowR) + (g.N >> 1) + blk * h + i;
+      sc_store(bytes, v); st32(scal + slot * 32, bytes); pidx[slot] = hidx[idx]; }
+    if (idx == 0) { pidx[rowL + g.N] = BP_POINT_DYNAMIC | p; pidx[rowR + g.N] = BP_POINT_DYNAMIC | p; }
+}
+// apply the round's challenge: a' = a_L u + u^-1 a_R, b' = b_L u^-1 + u b_R (:125-126,175-176); cG *= u^-1 (left) / u (right), cH *= u / u^-1 (:127-134,177-178)
+__global__ void __launch_bounds__(128) k_ippx_fold(ippx_geom g, const uint8_t *__restrict__ u_bytes, const uint8_t *__restrict__ uinv_bytes, sc *__restrict__ a, sc *__restrict__ b,
+                                                   sc *__restrict__ cG, sc *__restrict__ cH) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)g.B * g.N) return;
+    const uint32_t p = (uint32_t)(t / g.N), idx = (uint32_t)(t % g.N), h = g.n >> 1, pos = idx & (g.n - 1);
+    const sc u = sc_to_mont(sc_load(u_bytes + 32 * p)), ui = sc_to_mont(sc_load(uinv_bytes + 32 * p));
+    cG[t] = sc_mont_mul(cG[t], pos < h ? ui : u);
+    cH[t] = sc_mont_mul(cH[t], pos < h ? u : ui);
+    if (idx < h) {
+        sc *ap = a + (size_t)p * g.N, *bp_ = b + (size_t)p * g.N;
+        ap[idx] = sc_add(sc_mont_mul(ap[idx], u), sc_mont_mul(ui, ap[h + idx]));
+        bp_[idx] = sc_add(sc_mont_mul(bp_[idx], ui), sc_mont_mul(u, bp_[h + idx]));
+    }
+}
+__global__ void k_ippx_final(ippx_geom g, const sc *__restrict__ a, const sc *__restrict__ b, uint8_t *__restrict__ out) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= g.B) return;
+    uint8_t bytes[32];
+    sc_store(bytes, sc_from_mont(a[(size_t)p * g.N])); st32(out + 64 * p, bytes);
+    sc_store(bytes, sc_from_mont(b[(size_t)p * g.N])); st32(out + 64 * p + 32, bytes);
 }
 // copy table entries (by index) into a contiguous device vector: G(n,m) / H(n,m) slices for the IPP prover
 __global__ void k_gather_niels(const ge_niels *__restrict__ table, const uint32_t *__restrict__ idx, uint32_t n, ge_niels *__restrict__ out) {
@@ -570,7 +664,84 @@ __global__ void __launch_bounds__(32 * RP_HEAD_WARPS) k_rp_head(const rp_params 
         }
     }
 }
-// K5: verification scalars, fully data-parallel: one thread per (proof, term) with term in
+// Lean head: ONE thread per proof runs the sequential statement (rp_scalars_head) -- ~180 dependent Montgomery products.  Several
+// groups are in flight, so a head's latency is hidden; what counts is its footprint: one warp per 32 proofs here against eight
+// (a 256-thread block at 100 registers per 32 proofs = two thirds of the GPU's register file for a whole group) in k_rp_head.
+__global__ void __launch_bounds__(32) k_rp_head_seq(const rp_params *__restrict__ par, rp_geom g, const uint8_t *__restrict__ raw, uint32_t total,
+                                                    rp_head *__restrict__ heads, sc *__restrict__ tabs, const sc *__restrict__ pow2, uint32_t *__restrict__ status) {
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= total) return;
+    rp_head &h = heads[p];
+    uint32_t st = status[p];
+    if (st != BP_PROOF_OK) { h.status = st; return; }
+    const uint8_t *rw = raw + (size_t)p * (RP_RAW_U + g.k) * 64;
+    rp_challenges ch;
+    ch.y = rp_wide(rw + 64 * RP_RAW_Y); ch.z = rp_wide(rw + 64 * RP_RAW_Z); ch.x = rp_wide(rw + 64 * RP_RAW_X); ch.w = rp_wide(rw + 64 * RP_RAW_W);
+    ch.c = rp_wide(rw + 64 * RP_RAW_C); ch.rho = rp_wide(rw + 64 * RP_RAW_RHO);
+    bool bad = sc_is_zero(ch.y);
+    for (uint32_t j = 0; j < g.k; j++) { ch.u[j] = rp_wide(rw + 64 * (RP_RAW_U + j)); bad = bad || sc_is_zero(ch.u[j]); }
+    if (bad) { status[p] = BP_PROOF_VERIFICATION_ERROR; h.status = BP_PROOF_VERIFICATION_ERROR; return; }      // zero challenge: see rp_transcript
+    if (sc_is_zero(ch.rho)) ch.rho = sc_mont_one();
+    rp_scalars_head(h, tabs + (size_t)p * rp_tab_size(g.k, g.m), pow2, ch, par->proofs + (size_t)p * g.proof_len, g.k, g.n, g.m);
+    h.status = BP_PROOF_OK;
+}
+// K5 (combined check): verification scalars with the sum over the proofs taken in registers.  Block = (chunk of RP_CHUNK proofs of one
+// batch); thread = generator index i: it walks the chunk's proofs and adds up their weighted g_i and h_i (three Montgomery products
+// per proof and index), so the count x S per-proof array of the per-proof form below is never written; k_rp_static_reduce then adds
+// the few per-chunk partial sums.  The same block also writes the chunk's per-proof ("dynamic") scalars into the MSM scalar array.
+#define RP_CHUNK 32
+__global__ void __launch_bounds__(128) k_rp_scalars_sum(rp_geom g, const rp_head *__restrict__ heads, const sc *__restrict__ tabs, const uint32_t *__restrict__ dec_bad,
+                                                        sc *__restrict__ part, uint8_t *__restrict__ scal) {
+    __shared__ uint32_t okmask;
+    const uint32_t nchunks = (g.count + RP_CHUNK - 1) / RP_CHUNK, b = blockIdx.x / nchunks, ch = blockIdx.x % nchunks;
+    const uint32_t q0 = ch * RP_CHUNK, nq = min((uint32_t)RP_CHUNK, g.count - q0), p0 = b * g.count + q0;
+    if (threadIdx.x < 32) {
+        bool ok = threadIdx.x < nq && heads[p0 + threadIdx.x].status == BP_PROOF_OK && !dec_bad[p0 + threadIdx.x];
+        uint32_t m_ = __ballot_sync(0xffffffffu, ok);
+        if (threadIdx.x == 0) okmask = m_;
+    }
+    __syncthreads();
+    const uint32_t mask = okmask, tsz = rp_tab_size(g.k, g.m);
+    sc *mine = part + ((size_t)b * nchunks + ch) * g.S;
+    // weighted g_i = -zL - A_hi[hi] s_lo[lo],  h_i = zL + P_hi[hi] P_lo[lo] - Q_hi[hi] Q_lo[lo]  (rp_scalars_gh): the three products of the
+    // chunk's proofs are summed as 512-bit integers and reduced once per chunk (RP_CHUNK <= 32 products fit), one third of the multiplies
+    const uint32_t kl = rp_kl(g.k), TL = 1u << kl;
+    for (uint32_t i = threadIdx.x; i < g.N; i += blockDim.x) {
+        const uint32_t lo = i & (TL - 1), hi = i >> kl;
+        sc zsum = sc_zero();
+        sc_wide accA = sc_wide_zero(), accP = sc_wide_zero(), accQ = sc_wide_zero();
+        for (uint32_t q = 0; q < nq; q++) {
+            if (!((mask >> q) & 1u)) continue;
+            rp_tabs T = rp_tab_ptrs(const_cast<sc *>(tabs) + (size_t)(p0 + q) * tsz, g.k);
+            zsum = sc_add(zsum, heads[p0 + q].zL);
+            sc_wide_mac(accA, T.A_hi[hi], T.s_lo[lo]); sc_wide_mac(accP, T.P_hi[hi], T.P_lo[lo]); sc_wide_mac(accQ, T.Q_hi[hi], T.Q_lo[lo]);
+        }
+        mine[2 + i] = sc_sub(sc_neg(zsum), sc_wide_redc(accA));
+        mine[2 + g.N + i] = sc_sub(sc_add(zsum, sc_wide_redc(accP)), sc_wide_redc(accQ));
+    }
+    if (threadIdx.x < 2) {
+        sc s0 = sc_zero();
+        for (uint32_t q = 0; q < nq; q++) if ((mask >> q) & 1u) s0 = sc_add(s0, threadIdx.x == 0 ? heads[p0 + q].blinding_scalar : heads[p0 + q].basepoint_scalar);
+        mine[threadIdx.x] = s0;
+    }
+    for (uint32_t e = threadIdx.x; e < nq * g.D; e += blockDim.x) {
+        uint32_t q = e / g.D, d = e % g.D;
+        sc v = ((mask >> q) & 1u) ? sc_from_mont(rp_scalars_dynamic(heads[p0 + q], d, g.k)) : sc_zero();
+        uint8_t bytes[32]; sc_store(bytes, v); st32(scal + ((size_t)b * g.T + g.S + (size_t)(q0 + q) * g.D + d) * 32, bytes);
+    }
+}
+// add the per-chunk partial sums of a batch's static-term scalars: one warp per (static term, batch)
+__global__ void __launch_bounds__(32) k_rp_static_sum(const sc *__restrict__ part, rp_geom g, uint8_t *__restrict__ scal) {
+    const uint32_t nchunks = (g.count + RP_CHUNK - 1) / RP_CHUNK, s = blockIdx.x, b = blockIdx.y;
+    sc acc = sc_zero();
+    for (uint32_t c = threadIdx.x; c < nchunks; c += 32) acc = sc_add(acc, part[((size_t)b * nchunks + c) * g.S + s]);
+    for (int d = 16; d >= 1; d >>= 1) {
+        sc o; for (int i = 0; i < 8; i++) o.v[i] = __shfl_down_sync(0xffffffffu, acc.v[i], d);
+        acc = sc_add(acc, o);
+    }
+    if (threadIdx.x == 0) { uint8_t bytes[32]; sc_store(bytes, sc_from_mont(acc)); st32(scal + ((size_t)b * g.T + s) * 32, bytes); }
+}
+// K5 (per-proof form, used by the fallback): one thread per (proof, term) with term in
 // [0, N) -> (g_i, h_i) and [N, N + D) -> the per-proof scalars.
 //   contrib : total x S Montgomery scalars (weighted static-term scalars: B~, B, G.., H..)
 //   scal    : nbatch x T canonical scalars, the MSM scalar arrays; the D scalars of proof q of batch b start at b*T + S + q*D
@@ -629,6 +800,38 @@ __global__ void __launch_bounds__(128) k_rp_static_reduce(const sc *__restrict__
         for (uint32_t k = 1; k < (blockDim.x >> 5); k++) acc = sc_add(acc, sm[k]);
         uint8_t bytes[32]; sc_store(bytes, sc_from_mont(acc)); st32(scal + ((size_t)b * g.T + s) * 32, bytes);
     }
+}
+// fallback, first level: one combined MSM per chunk of RP_CHUNK proofs of a failing batch.  Everything is already there: the chunk's
+// summed static-term scalars (k_rp_scalars_sum's partial sums) and its proofs' dynamic scalars.  Rows are [S static | RP_CHUNK*D dynamic],
+// the tail of a short last chunk padded with zero scalars (a zero scalar never touches its point).
+__global__ void k_rp_chunk_rows(const sc *__restrict__ part_b, const uint8_t *__restrict__ dyn_b, rp_geom g, uint32_t gens_cap, uint32_t gens_parties, uint32_t dyn_base,
+                                uint8_t *__restrict__ out_scalars, uint32_t *__restrict__ out_pidx) {
+    const uint32_t nchunks = (g.count + RP_CHUNK - 1) / RP_CHUNK, row = g.S + RP_CHUNK * g.D;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)nchunks * row) return;
+    uint32_t ch = (uint32_t)(i / row), t = (uint32_t)(i % row);
+    uint8_t b[32]; uint32_t v;
+    if (t < g.S) {
+        sc_store(b, sc_from_mont(part_b[(size_t)ch * g.S + t]));
+        if (t < 2) v = t;
+        else if (t < 2 + g.N) { uint32_t q = t - 2; v = 2 + (q / g.n) * gens_cap + (q % g.n); }
+        else { uint32_t q = t - 2 - g.N; v = 2 + gens_parties * gens_cap + (q / g.n) * gens_cap + (q % g.n); }
+    } else {
+        uint32_t e = t - g.S, q = ch * RP_CHUNK + e / g.D;
+        if (q < g.count) { ld32(b, dyn_b + ((size_t)q * g.D + e % g.D) * 32); v = BP_POINT_DYNAMIC | (dyn_base + q * g.D + e % g.D); }
+        else { for (int j = 0; j < 32; j++) b[j] = 0; v = 0; }
+    }
+    st32(out_scalars + 32 * i, b); out_pidx[i] = v;
+}
+// verdicts of the proofs in chunks whose combined check passed (the failing chunks are re-checked proof by proof); chunk_ok[ch] = identity flags
+__global__ void k_rp_verdict_chunks(const uint32_t *__restrict__ status, const uint32_t *__restrict__ dec_bad, const ge_ext *__restrict__ results, uint32_t count,
+                                    uint32_t *__restrict__ verdict, uint32_t *__restrict__ chunk_ok) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= count) return;
+    uint32_t ch = q / RP_CHUNK;
+    bool ok = ge_is_identity(ld_ext(results + ch));
+    if (q % RP_CHUNK == 0) chunk_ok[ch] = ok ? 1u : 0u;
+    if (ok) verdict[q] = rp_eff_status(status[q], dec_bad[q]);
 }
 // fallback: expand contrib (Montgomery) into per-proof canonical scalar rows [S static | D dynamic] for the proofs of one batch;
 // contrib / dyn_scalars point at the batch's first proof

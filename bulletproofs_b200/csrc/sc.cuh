@@ -86,6 +86,32 @@ BP_HD sc sc_mont_mul(const sc &a, const sc &b) {
     return sc_cond_sub_l(r);                      // t < 2l
 #endif
 }
+// Lazy reduction for sums of products: acc (16 limbs) += a*b without reducing, then one Montgomery reduction of the sum.
+// Up to 32 products of values < l fit: 32 l^2 < 2^512, and REDC(T) = (T + M l)/R < T/R + l < 3l for T < 32 l^2 (R = 2^256 ~ 16 l).
+struct sc_wide { uint32_t v[16]; };
+BP_HD sc_wide sc_wide_zero() { sc_wide r; for (int i = 0; i < 16; i++) r.v[i] = 0; return r; }
+BP_HD void sc_wide_mac(sc_wide &acc, const sc &a, const sc &b) {
+    fe fa, fb;
+    for (int i = 0; i < 8; i++) { fa.v[i] = a.v[i]; fb.v[i] = b.v[i]; }
+    uint32_t t[16];
+    fe_mul_wide(t, fa, fb);
+    uint64_t c = 0;
+    for (int i = 0; i < 16; i++) { c += (uint64_t)acc.v[i] + t[i]; acc.v[i] = (uint32_t)c; c >>= 32; }
+}
+// T/R mod l for T < 32 l^2, result < l
+BP_HD sc sc_wide_redc(const sc_wide &T) {
+    fe fl = fe{SC_L_LIMBS}, flp = fe{SC_LPRIME_LIMBS}, tl;
+    for (int i = 0; i < 8; i++) tl.v[i] = T.v[i];
+    uint32_t q[16], u[16];
+    fe_mul_wide(q, tl, flp);
+    fe M; for (int i = 0; i < 8; i++) M.v[i] = q[i];
+    fe_mul_wide(u, M, fl);
+    uint32_t nz = 0; for (int i = 0; i < 8; i++) nz |= T.v[i];
+    uint64_t c = nz ? 1 : 0;
+    sc r;
+    for (int i = 0; i < 8; i++) { c += (uint64_t)T.v[8 + i] + u[8 + i]; r.v[i] = (uint32_t)c; c >>= 32; }
+    return sc_cond_sub_l(sc_cond_sub_l(r));       // < 3l before, c is zero (3l < 2^254)
+}
 BP_HD sc sc_to_mont(const sc &a) { return sc_mont_mul(a, sc{SC_RR_LIMBS}); }
 BP_HD sc sc_from_mont(const sc &a) { sc one = sc_zero(); one.v[0] = 1; return sc_mont_mul(a, one); }
 BP_HD sc sc_mont_from_u64(uint64_t x) { sc t = sc_zero(); t.v[0] = (uint32_t)x; t.v[1] = (uint32_t)(x >> 32); return sc_to_mont(t); }

@@ -107,6 +107,51 @@ int bp_ipp_lr(bp_ipp *sess, size_t n_half, const uint8_t *scalars_L, const uint8
 int bp_ipp_fold(bp_ipp *sess, size_t n_half, const uint8_t *g_lo, const uint8_t *g_hi, const uint8_t *h_lo, const uint8_t *h_hi, int per_index);
 void bp_ipp_end(bp_ipp *sess);
 
+/* ---- point values across the boundary ------------------------------------------------------- */
+/* CompressedRistretto::decompress() -> Option<RistrettoPoint> for n points (call sites src/range_proof/mod.rs:433-443,
+ * src/inner_product_proof.rs:296-306, src/r1cs/verifier.rs:482): xyzt_out[i] = the extended coordinates X | Y | Z | T of point i as
+ * four canonical 32-byte field elements (Z = 1) -- an in-memory RistrettoPoint a host caller can keep; ok[i] = 0 where the
+ * reference would return None (the slot then holds the identity).  bp_compress_batch is RistrettoPoint::compress()
+ * (src/inner_product_proof.rs:99,113, src/range_proof/dealer.rs:113-116) on such values (any projective representative). */
+int bp_decompress_batch(bp_ctx *ctx, const uint8_t *points, size_t n, uint8_t *xyzt_out, uint8_t *ok);
+int bp_compress_batch(bp_ctx *ctx, const uint8_t *xyzt, size_t n, uint8_t *points_out);
+
+/* ---- resident point sets ------------------------------------------------------------------- */
+/* A vector of n points decompressed once and kept on the device (affine Niels form, 96 B/point): the bases of repeated MSMs
+ * (`Vec<RistrettoPoint>` reused across vartime_multiscalar_mul calls, e.g. the generator vectors of inner_product_proof.rs:87-178).
+ * BP_ERR_INVALID_POINT if any encoding is invalid. */
+typedef struct bp_points bp_points;
+int bp_points_create(bp_ctx *ctx, const uint8_t *points, size_t n, bp_points **out);
+int bp_points_create_device(bp_ctx *ctx, const void *d_points, size_t n, bp_points **out);
+void bp_points_destroy(bp_points *set);
+size_t bp_points_count(const bp_points *set);
+/* n_msm MSMs of `terms` terms each over the first `terms` points of the set; MSM j takes scalars[j*terms .. (j+1)*terms).
+ * Device form: d_scalars / d_outs (n_msm x 32 B) / d_status (n_msm bytes, optional) are device pointers, nothing is synchronised.
+ * Host form: pinned memory recommended; synchronises. */
+int bp_msm_points_device(bp_ctx *ctx, bp_points *set, const void *d_scalars, size_t n_msm, size_t terms, void *d_outs, void *d_status);
+int bp_msm_points(bp_ctx *ctx, bp_points *set, const uint8_t *scalars, size_t n_msm, size_t terms, uint8_t *outs, uint8_t *status);
+
+/* ---- inner-product prover, device-resident (no generator folding) ---------------------------- */
+/* InnerProductProof::create (src/inner_product_proof.rs:38-193) for n_proofs proofs of the same length N side by side.  The vectors
+ * a, b, G_factors, H_factors stay on the device; the points are never folded -- round j's L and R are MSMs of N + 1 terms over the
+ * ORIGINAL generators with the accumulated challenge products as coefficients (same group elements, hence the same proof bytes, as
+ * the reference's folded form :127-134,177-178) -- so a round is O(N) scalar products and one MSM launch chain for all proofs.
+ * The host keeps the transcripts: round() returns L, R (:87-113,153-163), the caller appends them, draws u (:118-121,168-171) and
+ * calls fold(u, u^-1) (:122-134,172-178); after lg N rounds finish() returns the final a, b (:187-192).
+ *   begin        : G, H = BulletproofGens::G(n, m) / H(n, m) of the resident table, N = n*m
+ *   begin_points : arbitrary G, H (N compressed points each)
+ *   Q  : n_proofs x 32 B;  a, b : n_proofs x N canonical scalars;  G_factors / H_factors : likewise, or NULL for all ones. */
+typedef struct bp_ippx bp_ippx;
+int bp_ippx_begin(bp_ctx *ctx, bp_gens *gens, size_t n, size_t m, size_t n_proofs, const uint8_t *Q, const uint8_t *G_factors, const uint8_t *H_factors,
+                  const uint8_t *a, const uint8_t *b, bp_ippx **out);
+int bp_ippx_begin_points(bp_ctx *ctx, const uint8_t *G, const uint8_t *H, size_t N, size_t n_proofs, const uint8_t *Q, const uint8_t *G_factors, const uint8_t *H_factors,
+                         const uint8_t *a, const uint8_t *b, bp_ippx **out);
+size_t bp_ippx_current_len(const bp_ippx *sess);
+int bp_ippx_round(bp_ippx *sess, uint8_t *LR_out /* n_proofs x 64 */);
+int bp_ippx_fold(bp_ippx *sess, const uint8_t *u /* n_proofs x 32 */, const uint8_t *u_inv);
+int bp_ippx_finish(bp_ippx *sess, uint8_t *ab_out /* n_proofs x 64 */);
+void bp_ippx_end(bp_ippx *sess);
+
 /* ---- generator tables ---------------------------------------------------------------------- */
 /* BulletproofGens::new(gens_capacity, party_capacity) + PedersenGens::default()
  * (generators.rs:44-53,157-204): SHAKE256 expansion on the host, Elligator maps and the

@@ -560,6 +560,12 @@ void orc_from_uniform_bytes(const uint8_t in[64], uint8_t out[32]) { ge_init_con
 void orc_scalar_from_wide(const uint8_t in[64], uint8_t out[32]) { sc s; sc_from_bytes_wide(&s, in); sc_tobytes(out, &s); }
 void orc_scalar_mul(const uint8_t a[32], const uint8_t b[32], uint8_t out[32]) { sc x, y; sc_from_bytes_mod_order(&x, a); sc_from_bytes_mod_order(&y, b); sc_mul(&x, &x, &y); sc_tobytes(out, &x); }
 void orc_scalar_invert(const uint8_t a[32], uint8_t out[32]) { sc x; sc_from_bytes_mod_order(&x, a); sc_invert(&x, &x); sc_tobytes(out, &x); }
+/* count uniform scalars: consecutive 64-byte blocks of ChaCha20(seed) wide-reduced mod l (Scalar::random with a ChaChaRng), skipping `skip` scalars first */
+void orc_scalars_from_chacha(const uint8_t seed[32], size_t skip, size_t count, uint8_t *out) {
+    chacha_rng r; chacha_seed(&r, seed); uint8_t b[64]; sc s;
+    for (size_t i = 0; i < skip; i++) chacha_fill(&r, b, 64);
+    for (size_t i = 0; i < count; i++) { chacha_fill(&r, b, 64); sc_from_bytes_wide(&s, b); sc_tobytes(out + 32 * i, &s); }
+}
 void orc_chacha_fill(const uint8_t seed[32], uint8_t *out, size_t n) { chacha_rng r; chacha_seed(&r, seed); chacha_fill(&r, out, n); }
 void orc_sha3_512(const uint8_t *in, size_t n, uint8_t out[64]) { sha3_512(out, in, n); }
 void orc_shake256(const uint8_t *in, size_t n, uint8_t *out, size_t outlen) { sponge s; shake256_init(&s); sponge_absorb(&s, in, n); sponge_squeeze(&s, out, outlen); }

@@ -50,6 +50,12 @@ int emul_is_identity_of_diff(const uint8_t *a, const uint8_t *b) {   // a - b in
 void emul_sc_mul(const uint8_t *a, const uint8_t *b, uint8_t *out) {
     sc x = sc_to_mont(sc_load(a)), y = sc_to_mont(sc_load(b)); sc_store(out, sc_from_mont(sc_mont_mul(x, y)));
 }
+// sum of n <= 32 products through the lazy-reduction accumulator (sc_wide_mac / sc_wide_redc), canonical bytes in and out
+void emul_sc_sum_products(const uint8_t *a, const uint8_t *b, uint32_t n, uint8_t *out) {
+    sc_wide acc = sc_wide_zero();
+    for (uint32_t i = 0; i < n; i++) sc_wide_mac(acc, sc_to_mont(sc_load(a + 32 * i)), sc_to_mont(sc_load(b + 32 * i)));
+    sc_store(out, sc_from_mont(sc_wide_redc(acc)));
+}
 void emul_sc_addsub(const uint8_t *a, const uint8_t *b, int sub, uint8_t *out) { sc x = sc_load(a), y = sc_load(b); sc_store(out, sub ? sc_sub(x, y) : sc_add(x, y)); }
 void emul_sc_invert(const uint8_t *a, uint8_t *out) { sc_store(out, sc_from_mont(sc_mont_invert(sc_to_mont(sc_load(a))))); }
 void emul_sc_from_wide(const uint8_t *in, uint8_t *out) { sc_store(out, sc_from_mont(sc_mont_from_wide(in))); }

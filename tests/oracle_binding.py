@@ -122,6 +122,12 @@ class Oracle:
         self.L.orc_rangeproof_verify_rlc(g, tstate, proofs, plen, Vs, m, n, count, seed, nthreads, st)
         return list(st.raw)
 
+    def scalars_from_chacha(self, seed, count, skip=0):
+        self.L.orc_scalars_from_chacha.argtypes = [_p, _sz, _sz, _p]
+        out = ctypes.create_string_buffer(32 * count)
+        self.L.orc_scalars_from_chacha(seed, skip, count, out)
+        return out.raw
+
     # MSM field backends (oracle/vec4_*.h): "u64", "avx2", "ifma", "auto"; process-wide, not thread-safe
     def set_backend(self, name):
         self.L.orc_set_backend.argtypes = [_p]

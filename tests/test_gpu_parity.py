@@ -365,3 +365,41 @@ def test_pending_verification_blocks_other_entry_points(gpu_ctx, orc):
     assert [i for i, v in enumerate(got) if v] == [2]
     assert gpu_ctx.msm(le(1), orc.from_uniform(bytes(64)))[0] == 0
     gens.close()
+
+
+def test_point_values_cross_the_boundary(gpu_ctx, orc):
+    """bp_decompress_batch / bp_compress_batch: CompressedRistretto::decompress -> Option<RistrettoPoint> and back (SURVEY.md 8b)."""
+    rnd = random.Random(21)
+    pts = [orc.from_uniform(rnd.randbytes(64)) for _ in range(200)] + [bytes(32)]
+    bad = [b"\x01" + bytes(31), le(p), le(p - 1), b"\xff" * 32]
+    xyzt, ok = gpu_ctx.decompress(b"".join(pts + bad))
+    assert ok == [orc.point_is_valid(q) for q in pts + bad] and ok[:len(pts)] == [1] * len(pts)
+    for v in xyzt[:len(pts)]:
+        X, Y, Z, T = (int.from_bytes(v[32 * i:32 * i + 32], "little") for i in range(4))
+        d = (-121665 * pow(121666, p - 2, p)) % p
+        assert Z == 1 and T == X * Y % p and (-X * X + Y * Y - 1 - d * X * X * Y * Y) % p == 0          # on the curve, extended coordinates consistent
+    assert gpu_ctx.compress(b"".join(xyzt[:len(pts)])) == b"".join(pts)
+    # any projective representative compresses to the same bytes
+    lam = 0x1234567
+    scaled = b"".join(le(int.from_bytes(v[32 * i:32 * i + 32], "little") * lam % p) for v in xyzt[:20] for i in range(4))
+    assert gpu_ctx.compress(scaled) == b"".join(pts[:20])
+
+
+@pytest.mark.parametrize("terms,n_msm", [(1, 3), (147, 5), (1000, 8), (4096, 2)])
+def test_resident_point_set_msm(gpu_ctx, orc, terms, n_msm):
+    """bp_points: bases decompressed once, many MSMs over them == the oracle's MSM on the same bytes."""
+    import bulletproofs_b200 as bp
+    rnd = random.Random(terms)
+    base = [orc.from_uniform(rnd.randbytes(64)) for _ in range(min(terms, 64))]
+    pts = b"".join(rnd.choice(base) for _ in range(terms + 3))
+    ps = bp.PointSet(gpu_ctx, pts)
+    sc = b"".join(le(rnd.randrange(l)) for _ in range(terms * n_msm))
+    st, outs = ps.msm(sc, n_msm, terms)
+    assert st == [0] * n_msm
+    for j in range(n_msm):
+        assert (0, outs[j]) == orc.msm(sc[32 * terms * j:32 * terms * (j + 1)], pts[:32 * terms]), j
+    st, outs2 = ps.msm(sc[:32 * terms], 1, terms)            # another shape on the same set
+    assert outs2[0] == outs[0]
+    ps.close()
+    with pytest.raises(bp.BpError):
+        bp.PointSet(gpu_ctx, pts[:64] + b"\x01" + bytes(31))

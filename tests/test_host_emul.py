@@ -62,6 +62,18 @@ def test_merlin(E, orc):
     assert orc.transcript(b"abc")[:203] == st3.raw
 
 
+def test_lazy_reduction_of_product_sums(E):
+    """sc_wide_mac / sc_wide_redc (k_rp_scalars_sum): up to 32 products summed as 512-bit integers, one Montgomery reduction"""
+    rnd = random.Random(12)
+    for n, mode in [(1, "rand"), (7, "rand"), (32, "rand"), (32, "max"), (32, "zero"), (31, "mixed")]:
+        if mode == "max": A = [l - 1] * n; B = [l - 1] * n
+        elif mode == "zero": A = [0] * n; B = [rnd.randrange(l) for _ in range(n)]
+        elif mode == "mixed": A = [rnd.choice([0, 1, l - 1, rnd.randrange(l)]) for _ in range(n)]; B = [rnd.choice([l - 1, l - 2, rnd.randrange(l)]) for _ in range(n)]
+        else: A = [rnd.randrange(l) for _ in range(n)]; B = [rnd.randrange(l) for _ in range(n)]
+        o = buf(); E.emul_sc_sum_products(b"".join(le(x) for x in A), b"".join(le(x) for x in B), n, o)
+        assert int.from_bytes(o.raw, "little") == sum(x * y for x, y in zip(A, B)) % l, (n, mode)
+
+
 def test_points(E, orc):
     rnd = random.Random(3)
     pts = []

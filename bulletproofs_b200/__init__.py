@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbpmsm.so")
+LIB_PATH = os.environ.get("BPMSM_LIB_EXPERIMENT") or os.path.join(_HERE, "libbpmsm.so")     # the override exists for A/B builds of the same source (benchmarks/)
 
 TRANSCRIPT_BYTES = 203
 OK, ERR_INVALID_POINT, ERR_LENGTH_MISMATCH, ERR_NONCANONICAL_SCALAR, ERR_CUDA, ERR_INVALID_ARGUMENT = range(6)
@@ -115,6 +115,8 @@ def host_lib():
         H = ctypes.CDLL(HOST_LIB_PATH)
         H.bph_rangeproof_prove.restype = _int
         H.bph_rangeproof_prove.argtypes = [_vp, _vp, _sz, _sz, _u8p, _c.POINTER(_c.c_uint64), _u8p, _sz, _sz, _u8p, _u8p, _u8p]
+        H.bph_rangeproof_prove_many.restype = _int
+        H.bph_rangeproof_prove_many.argtypes = [_vp, _vp, _sz, _sz, _u8p, _c.POINTER(_c.c_uint64), _u8p, _sz, _sz, _sz, _u8p, _u8p, _sz, _u8p, _u8p]
         H.bph_rangeproof_verify.restype = _int
         H.bph_rangeproof_verify.argtypes = [_vp, _vp, _sz, _sz, _u8p, _u8p, _sz, _u8p, _sz, _sz]
         H.bph_ipp_create.restype = _int
@@ -413,6 +415,20 @@ def prove_multiple(ctx: Context, gens: Gens, transcript: Transcript, values, bli
     if rc < 0:
         raise BpError(rc, lib().bp_last_error(ctx._h).decode())
     return rc, proof.raw, V.raw
+
+
+def prove_many(ctx: Context, gens: Gens, transcript: Transcript, values, blindings: bytes, n: int, m: int, rng_seeds: bytes):
+    """`count` = len(values) // m independent aggregated proofs with every group operation batched across the proofs (one device call per
+    prover phase, one inner-product session for all).  Proof p uses values[p*m:(p+1)*m] and ChaChaRng::from_seed(rng_seeds[32p:32p+32]);
+    every transcript starts from `transcript`.  Returns (status list, proofs bytes, commitments bytes) -- the same bytes as `count` prove_multiple calls."""
+    count = len(values) // m
+    vals = (ctypes.c_uint64 * len(values))(*values)
+    plen = rangeproof_size(n, m)
+    proofs = ctypes.create_string_buffer(plen * count); V = ctypes.create_string_buffer(32 * m * count); st = ctypes.create_string_buffer(count)
+    rc = host_lib().bph_rangeproof_prove_many(ctx._h, gens._h, gens.gens_capacity, gens.party_capacity, transcript.to_bytes(), vals, blindings, m, n, count, rng_seeds, proofs, plen, V, st)
+    if rc < 0:
+        raise BpError(rc, lib().bp_last_error(ctx._h).decode())
+    return list(st.raw), proofs.raw, V.raw
 
 
 def verify_multiple(ctx: Context, gens: Gens, transcript: Transcript, proof: bytes, commitments: bytes, n: int) -> int:

@@ -42,7 +42,7 @@ def build_host(force=False):
     lib = os.path.join(ROOT, "bulletproofs_b200", "libbulletproofs_host.so")
     srcs = [os.path.join(hdir, f) for f in os.listdir(hdir)] + [os.path.join(CSRC, f) for f in ("sc.cuh", "merlin.cuh", "fe.cuh")] + [LIB]
     if force or not _newer(lib, srcs):
-        _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", lib, os.path.join(hdir, "bulletproofs.cpp"), os.path.join(hdir, "r1cs.cpp"), os.path.join(hdir, "mpc.cpp"),
+        _run(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-o", lib, os.path.join(hdir, "bulletproofs.cpp"), os.path.join(hdir, "r1cs.cpp"), os.path.join(hdir, "mpc.cpp"),
               "-L" + os.path.join(ROOT, "bulletproofs_b200"), "-lbpmsm", "-Wl,-rpath,$ORIGIN"])
     return lib
 
@@ -61,7 +61,7 @@ def build_emul(force=False):
     lib = os.path.join(edir, "libemul.so")
     srcs = [os.path.join(edir, "emul.cpp")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     if force or not _newer(lib, srcs):
-        _run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", lib, os.path.join(edir, "emul.cpp")])
+        _run(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-o", lib, os.path.join(edir, "emul.cpp")])
     return lib
 
 

@@ -257,6 +257,9 @@ int bp_ctx_create(int device, void *stream, bp_ctx **out) {
     if (cudaMallocHost((void **)&c->h_stage, 512 * bp_ctx::STAGE_SLOTS) != cudaSuccess) { cudaFreeHost(c->h_flag); delete c; return BP_ERR_CUDA; }
     for (int i = 0; i < bp_ctx::STAGE_SLOTS; i++) cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking);
+    // the per-proof kernels stage their block's proofs in dynamic shared memory: up to 32 proofs of 32*(9+2*20) + 32*m bytes
+    cudaFuncSetAttribute(k_rp_transcript, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(k_rp_decompress, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     *out = c;
     return BP_OK;
@@ -622,14 +625,16 @@ static int rp_chain(bp_ctx *c, bp_gens *gens, const rp_geom &g) {
     {   // branch 2
         cudaStream_t keep = c->stream; c->stream = s2;          // LAUNCH brackets its events on ctx->stream
         int rc = [&]() -> int {
-            LAUNCH(c, KID_RP_DECOMPRESS, k_rp_decompress<<<blocks_for((size_t)total * g.D, 128), 128, 0, s2>>>(par, g, total, c->rp_niels.as<ge_niels>(), c->rp_decbad.as<uint32_t>()));
+            const size_t dec_smem = (size_t)(RP_DEC_THREADS / g.D + 2) * (g.proof_len + 32 * g.m);
+            LAUNCH(c, KID_RP_DECOMPRESS, k_rp_decompress<<<blocks_for((size_t)total * g.D, RP_DEC_THREADS), RP_DEC_THREADS, dec_smem, s2>>>(par, g, total, c->rp_niels.as<ge_niels>(), c->rp_decbad.as<uint32_t>()));
             return BP_OK;
         }();
         c->stream = keep;
         if (rc) return rc;
     }
     if (s2 != s) CK(c, cudaEventRecord(c->ev_join, s2));
-    LAUNCH(c, KID_RP_TRANSCRIPT, k_rp_transcript<<<blocks_for(total, RP_TR_THREADS), RP_TR_THREADS, 0, s>>>(par, g, total, c->rp_raw.as<uint8_t>(), c->rp_status.as<uint32_t>()));
+    const size_t tr_smem = RP_TR_ROWS_BYTES + (size_t)RP_TR_THREADS * (g.proof_len + 32 * g.m);
+    LAUNCH(c, KID_RP_TRANSCRIPT, k_rp_transcript<<<blocks_for(total, RP_TR_THREADS), RP_TR_THREADS, tr_smem, s>>>(par, g, total, c->rp_raw.as<uint8_t>(), c->rp_status.as<uint32_t>()));
     LAUNCH(c, KID_RP_HEAD, k_rp_head_seq<<<blocks_for(total, 32), 32, 0, s>>>(par, g, c->rp_raw.as<uint8_t>(), total, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(),
                                                                                   c->pow2_tab.as<sc>(), c->rp_status.as<uint32_t>()));
     if (s2 != s) CK(c, cudaStreamWaitEvent(s, c->ev_join, 0));

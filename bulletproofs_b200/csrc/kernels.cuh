@@ -79,6 +79,36 @@ __device__ __forceinline__ void tma_stage_tile(void *smem_dst, const void *gsrc,
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(b) : "memory");
     } while (!done);
 }
+// Two-source form for the per-proof kernels: a block's slice of the proof array and of the commitment array (both contiguous,
+// 16-byte aligned when the caller's buffers are) land in shared memory through two bulk copies signalled on one mbarrier; the
+// threads then take their 32-byte fields -- at offsets that are not 16-byte aligned in general -- from shared memory.
+// Falls back to a cooperative copy for buffers that are not 16-byte aligned.
+__device__ __forceinline__ void tma_stage_two(uint8_t *dst_a, const uint8_t *src_a, uint32_t bytes_a, uint8_t *dst_b, const uint8_t *src_b, uint32_t bytes_b, uint64_t *bar) {
+    const bool aligned = ((reinterpret_cast<uintptr_t>(src_a) | reinterpret_cast<uintptr_t>(src_b) | bytes_a | bytes_b) & 15) == 0;
+    if (!aligned) {
+        for (uint32_t i = threadIdx.x; i < bytes_a; i += blockDim.x) dst_a[i] = src_a[i];
+        for (uint32_t i = threadIdx.x; i < bytes_b; i += blockDim.x) dst_b[i] = src_b[i];
+        __syncthreads();
+        return;
+    }
+    uint32_t b = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes_a + bytes_b) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst_a)), "l"(src_a), "r"(bytes_a), "r"(b) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(dst_b)), "l"(src_b), "r"(bytes_b), "r"(b) : "memory");
+    }
+    uint32_t done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(b) : "memory");
+    } while (!done);
+}
 __device__ __forceinline__ void lds32(uint8_t dst[32], const uint8_t *smem_src) {
     const uint4 *p = reinterpret_cast<const uint4 *>(smem_src);
     uint4 a = p[0], b = p[1];
@@ -563,17 +593,23 @@ __device__ __forceinline__ uint32_t rp_eff_status(uint32_t st, uint32_t dec_bad)
     return st != BP_PROOF_OK ? st : (dec_bad ? (uint32_t)BP_PROOF_VERIFICATION_ERROR : (uint32_t)BP_PROOF_OK);
 }
 
-// K6: transcript replay (pure hashing).  One thread per proof (32 proofs per warp, identical control flow, every lane busy);
-// the STROBE state of each thread is a padded shared-memory row (stride 204 B: conflict-free byte access).
+// K6: transcript replay (pure hashing).  One thread per proof (32 proofs per warp, identical control flow, every lane busy).  The block's
+// 32 proofs and their commitments are staged into shared memory by the TMA engine (two bulk copies, tma_stage_two): the replay reads
+// every proof byte once, one byte at a time at arbitrary offsets, which from shared memory costs an LDS instead of an L2 round trip.
+// The STROBE state of each thread is a padded shared-memory row (stride 204 B: conflict-free byte access).
 #define RP_TR_THREADS 32
+#define RP_TR_ROWS_BYTES 6656           // 32 x 204 rounded up to a multiple of 128
 __global__ void __launch_bounds__(RP_TR_THREADS) k_rp_transcript(const rp_params *__restrict__ par, rp_geom g, uint32_t total,
                                                                    uint8_t *__restrict__ raw, uint32_t *__restrict__ status) {
-    __shared__ __align__(16) uint8_t rows[RP_TR_THREADS][204];
-    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ __align__(128) uint8_t tr_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    uint8_t (*rows)[204] = reinterpret_cast<uint8_t (*)[204]>(tr_smem);
+    uint8_t *sp = tr_smem + RP_TR_ROWS_BYTES, *sv = sp + RP_TR_THREADS * g.proof_len;
+    const uint32_t p0 = blockIdx.x * blockDim.x, cnt = min((uint32_t)blockDim.x, total - p0), p = p0 + threadIdx.x;
+    tma_stage_two(sp, par->proofs + (size_t)p0 * g.proof_len, cnt * g.proof_len, sv, par->commitments + (size_t)p0 * g.m * 32, cnt * g.m * 32, &bar);
     if (p >= total) return;
-    const uint8_t *proof = par->proofs + (size_t)p * g.proof_len, *V = par->commitments + (size_t)p * g.m * 32;
     uint8_t (*my)[64] = reinterpret_cast<uint8_t (*)[64]>(raw + (size_t)p * (RP_RAW_U + g.k) * 64);
-    status[p] = rp_transcript_raw(my, proof, g.k, V, g.n, g.m, par->tstate, par->seed, rows[threadIdx.x]);
+    status[p] = rp_transcript_raw(my, sp + threadIdx.x * g.proof_len, g.k, sv + threadIdx.x * g.m * 32, g.n, g.m, par->tstate, par->seed, rows[threadIdx.x]);
 }
 // Cooperative head: the ~180 Montgomery products of one proof's shared scalars and tables (rp_scalars_head is the sequential
 // statement of the same values) are split over RP_HEAD_WARPS warps; lane = proof, so every warp runs one straight-line task
@@ -767,18 +803,25 @@ __global__ void __launch_bounds__(128) k_rp_scalars(rp_geom g, const rp_head *__
     }
 }
 // decompress the per-proof points in MSM order A,S,T_1,T_2,L..,R..,V.. straight out of the proof bytes; independent of the
-// transcript, so it runs beside k_rp_transcript / k_rp_head (second branch of the launch graph)
-__global__ void __launch_bounds__(128, 5) k_rp_decompress(const rp_params *__restrict__ par, rp_geom g, uint32_t total,
-                                                       ge_niels *__restrict__ out, uint32_t *__restrict__ dec_bad) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)total * g.D) return;
+// transcript, so it runs beside k_rp_transcript / k_rp_head_seq (second branch of the launch graph).  The proofs and commitments a
+// block's 128 points come from are contiguous: they are staged with two TMA bulk copies, the 32-byte encodings are read from shared memory.
+#define RP_DEC_THREADS 128
+__global__ void __launch_bounds__(RP_DEC_THREADS, 5) k_rp_decompress(const rp_params *__restrict__ par, rp_geom g, uint32_t total,
+                                                                  ge_niels *__restrict__ out, uint32_t *__restrict__ dec_bad) {
+    extern __shared__ __align__(128) uint8_t dec_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x, i = i0 + threadIdx.x, n_pts = (size_t)total * g.D;
+    const uint32_t pf = (uint32_t)(i0 / g.D), pl = (uint32_t)((min(i0 + blockDim.x, n_pts) - 1) / g.D), np = pl - pf + 1;     // proofs this block touches
+    uint8_t *sp = dec_smem, *sv = dec_smem + (size_t)(RP_DEC_THREADS / g.D + 2) * g.proof_len;
+    tma_stage_two(sp, par->proofs + (size_t)pf * g.proof_len, np * g.proof_len, sv, par->commitments + (size_t)pf * g.m * 32, np * g.m * 32, &bar);
+    if (i >= n_pts) return;
     uint32_t p = (uint32_t)(i / g.D), idx = (uint32_t)(i % g.D);
-    const uint8_t *proof = par->proofs + (size_t)p * g.proof_len, *src;
+    const uint8_t *proof = sp + (size_t)(p - pf) * g.proof_len, *src;
     if (idx < 4) src = proof + 32 * idx;
     else if (idx < 4 + g.k) src = proof + 224 + 64 * (idx - 4);
     else if (idx < 4 + 2 * g.k) src = proof + 224 + 64 * (idx - 4 - g.k) + 32;
-    else src = par->commitments + ((size_t)p * g.m + (idx - 4 - 2 * g.k)) * 32;
-    uint8_t s[32]; ld32_any(s, src);
+    else src = sv + ((size_t)(p - pf) * g.m + (idx - 4 - 2 * g.k)) * 32;
+    uint8_t s[32]; lds32(s, src);
     fe x, y; bool valid = ge_decode(x, y, s);
     st_niels(out + i, valid ? ge_to_niels_affine(x, y) : ge_niels_identity());
     if (!valid) dec_bad[p] = 1u;

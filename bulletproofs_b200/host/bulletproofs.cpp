@@ -20,12 +20,16 @@ void ChaChaRng::block() {
 }
 void ChaChaRng::fill_bytes(uint8_t *out, size_t n) { for (size_t i = 0; i < n; i++) { if (used_ == 64) block(); out[i] = buf_[used_++]; } }
 
-Scalar inner_product(const std::vector<Scalar> &a, const std::vector<Scalar> &b) {
-    if (a.size() != b.size()) throw std::invalid_argument("inner_product(a,b): lengths of vectors do not match");
-    Scalar out = Scalar::zero();
-    for (size_t i = 0; i < a.size(); i++) out += a[i] * b[i];
-    return out;
+Scalar inner_product(const std::vector<Scalar> &a, const std::vector<Scalar> &b) {       // inner_product_proof.rs:418-427
+    if (a.size() != b.size()) throw std::invalid_argument("inner_product: lengths differ");
+    const size_t n = a.size(), chunk = 4096;
+    if (n <= chunk) { Scalar acc = Scalar::zero(); for (size_t i = 0; i < n; i++) acc += a[i] * b[i]; return acc; }
+    std::vector<Scalar> part((n + chunk - 1) / chunk, Scalar::zero());        // long vectors (R1CS): partial sums over the host cores
+    parallel_for(part.size(), [&](size_t c) { Scalar acc = Scalar::zero(); for (size_t i = c * chunk; i < std::min(n, (c + 1) * chunk); i++) acc += a[i] * b[i]; part[c] = acc; });
+    Scalar acc = Scalar::zero(); for (const Scalar &x : part) acc += x;
+    return acc;
 }
+
 
 static void check(int rc, bp_ctx *ctx, const char *what) {
     if (rc == BP_OK) return;
@@ -34,61 +38,72 @@ static void check(int rc, bp_ctx *ctx, const char *what) {
 static std::vector<uint8_t> pack(const std::vector<Scalar> &v) { std::vector<uint8_t> o(32 * v.size()); for (size_t i = 0; i < v.size(); i++) v[i].write(o.data() + 32 * i); return o; }
 
 // ------------------------------------------------------------------ InnerProductProof::create
-// the round loop of inner_product_proof.rs:69-185 against a device session that holds G, H, Q
-static InnerProductProof ipp_rounds(bp_ipp *sess, bp_ctx *ctx, Transcript &t, const std::vector<Scalar> &Gf, const std::vector<Scalar> &Hf,
-                                    std::vector<Scalar> a, std::vector<Scalar> b) {
-    size_t n = a.size();
-    if (b.size() != n || Gf.size() != n || Hf.size() != n) throw std::invalid_argument("InnerProductProof::create: vector lengths differ");   // :59-64
-    if (n == 0 || (n & (n - 1))) throw std::invalid_argument("InnerProductProof::create: length must be a power of two");                    // :67
-    t.innerproduct_domain_sep(n);
-    InnerProductProof proof;
-    bool first = true;
+// The round loop of inner_product_proof.rs:69-185 against a device session that holds a, b, the factor / challenge coefficient vectors and
+// the (never folded) generators of B proofs of the same length: per round one bp_ippx_round (L, R of every proof), the transcripts on the
+// host, one bp_ippx_fold.  ts[p] is proof p's transcript.
+static std::vector<InnerProductProof> ipp_rounds_x(bp_ippx *sess, bp_ctx *ctx, std::vector<Transcript *> &ts, size_t n) {
+    size_t B = ts.size();
+    for (Transcript *t : ts) t->innerproduct_domain_sep(n);
+    std::vector<InnerProductProof> proofs(B);
+    std::vector<uint8_t> lr(64 * B), u(32 * B), ui(32 * B), ab(64 * B);
     while (n != 1) {
+        check(bp_ippx_round(sess, lr.data()), ctx, "bp_ippx_round");
+        parallel_for(B, [&](size_t p) {
+            CompressedRistretto L, R; memcpy(L.data(), lr.data() + 64 * p, 32); memcpy(R.data(), lr.data() + 64 * p + 32, 32);
+            proofs[p].L_vec.push_back(L); proofs[p].R_vec.push_back(R);
+            ts[p]->append_point("L", L); ts[p]->append_point("R", R);
+            Scalar c = ts[p]->challenge_scalar("u"), ci = c.invert();
+            Bytes32 cb = c.to_bytes(), cib = ci.to_bytes(); memcpy(u.data() + 32 * p, cb.data(), 32); memcpy(ui.data() + 32 * p, cib.data(), 32);
+        });
+        check(bp_ippx_fold(sess, u.data(), ui.data()), ctx, "bp_ippx_fold");
         n /= 2;
-        std::vector<Scalar> aL(a.begin(), a.begin() + n), aR(a.begin() + n, a.begin() + 2 * n), bL(b.begin(), b.begin() + n), bR(b.begin() + n, b.begin() + 2 * n);
-        Scalar c_L = inner_product(aL, bR), c_R = inner_product(aR, bL);
-        std::vector<Scalar> sL(2 * n + 1), sR(2 * n + 1);
-        for (size_t i = 0; i < n; i++) {
-            sL[i] = first ? aL[i] * Gf[n + i] : aL[i];        // a_L * g_R   over G_R       (:87-99 / :153-157)
-            sL[n + i] = first ? bR[i] * Hf[i] : bR[i];         // b_R * h_L   over H_L
-            sR[i] = first ? aR[i] * Gf[i] : aR[i];             // a_R * g_L   over G_L       (:101-113 / :159-163)
-            sR[n + i] = first ? bL[i] * Hf[n + i] : bL[i];     // b_L * h_R   over H_R
-        }
-        sL[2 * n] = c_L; sR[2 * n] = c_R;
-        CompressedRistretto L, R;
-        check(bp_ipp_lr(sess, n, pack(sL).data(), pack(sR).data(), L.data(), R.data()), ctx, "bp_ipp_lr");
-        proof.L_vec.push_back(L); proof.R_vec.push_back(R);
-        t.append_point("L", L); t.append_point("R", R);
-        Scalar u = t.challenge_scalar("u"), u_inv = u.invert();
-        std::vector<Scalar> g_lo(first ? n : 1), g_hi(first ? n : 1), h_lo(first ? n : 1), h_hi(first ? n : 1);
-        for (size_t i = 0; i < n; i++) {
-            a[i] = aL[i] * u + u_inv * aR[i];
-            b[i] = bL[i] * u_inv + u * bR[i];
-            if (first) { g_lo[i] = u_inv * Gf[i]; g_hi[i] = u * Gf[n + i]; h_lo[i] = u * Hf[i]; h_hi[i] = u_inv * Hf[n + i]; }     // :127-134
-        }
-        if (!first) { g_lo[0] = u_inv; g_hi[0] = u; h_lo[0] = u; h_hi[0] = u_inv; }                                                  // :177-178
-        check(bp_ipp_fold(sess, n, pack(g_lo).data(), pack(g_hi).data(), pack(h_lo).data(), pack(h_hi).data(), first ? 1 : 0), ctx, "bp_ipp_fold");
-        a.resize(n); b.resize(n);
-        first = false;
     }
-    proof.a = a[0]; proof.b = b[0];
-    return proof;
+    check(bp_ippx_finish(sess, ab.data()), ctx, "bp_ippx_finish");
+    for (size_t p = 0; p < B; p++)
+        if (!Scalar::from_canonical_bytes(ab.data() + 64 * p, proofs[p].a) || !Scalar::from_canonical_bytes(ab.data() + 64 * p + 32, proofs[p].b)) throw std::runtime_error("bp_ippx_finish: bad scalar");
+    return proofs;
+}
+static void ipp_check_lengths(size_t n, const std::vector<Scalar> &Gf, const std::vector<Scalar> &Hf, const std::vector<Scalar> &a, const std::vector<Scalar> &b) {
+    if (b.size() != n || Gf.size() != n || Hf.size() != n || a.size() != n) throw std::invalid_argument("InnerProductProof::create: vector lengths differ");   // :59-64
+    if (n == 0 || (n & (n - 1))) throw std::invalid_argument("InnerProductProof::create: length must be a power of two");                              // :67
 }
 
 InnerProductProof InnerProductProof::create(Device &dev, const BulletproofGens &gens, size_t n, size_t m, Transcript &t, const CompressedRistretto &Q,
                                             const std::vector<Scalar> &Gf, const std::vector<Scalar> &Hf, std::vector<Scalar> a, std::vector<Scalar> b) {
-    bp_ipp *sess = nullptr;
-    check(bp_ipp_begin(dev.ctx, gens.handle, n, m, Q.data(), &sess), dev.ctx, "bp_ipp_begin");
-    try { InnerProductProof p = ipp_rounds(sess, dev.ctx, t, Gf, Hf, std::move(a), std::move(b)); bp_ipp_end(sess); return p; }
-    catch (...) { bp_ipp_end(sess); throw; }
+    ipp_check_lengths(n * m, Gf, Hf, a, b);
+    bp_ippx *sess = nullptr;
+    check(bp_ippx_begin(dev.ctx, gens.handle, n, m, 1, Q.data(), pack(Gf).data(), pack(Hf).data(), pack(a).data(), pack(b).data(), &sess), dev.ctx, "bp_ippx_begin");
+    std::vector<Transcript *> ts = {&t};
+    try { InnerProductProof p = ipp_rounds_x(sess, dev.ctx, ts, n * m)[0]; bp_ippx_end(sess); return p; }
+    catch (...) { bp_ippx_end(sess); throw; }
 }
 InnerProductProof InnerProductProof::create(Device &dev, Transcript &t, const CompressedRistretto &Q, const std::vector<Scalar> &Gf, const std::vector<Scalar> &Hf,
                                             const std::vector<CompressedRistretto> &G, const std::vector<CompressedRistretto> &H, std::vector<Scalar> a, std::vector<Scalar> b) {
     if (G.size() != a.size() || H.size() != a.size()) throw std::invalid_argument("InnerProductProof::create: vector lengths differ");
-    bp_ipp *sess = nullptr;
-    check(bp_ipp_begin_points(dev.ctx, G[0].data(), H[0].data(), G.size(), Q.data(), &sess), dev.ctx, "bp_ipp_begin_points");
-    try { InnerProductProof p = ipp_rounds(sess, dev.ctx, t, Gf, Hf, std::move(a), std::move(b)); bp_ipp_end(sess); return p; }
-    catch (...) { bp_ipp_end(sess); throw; }
+    ipp_check_lengths(a.size(), Gf, Hf, a, b);
+    bp_ippx *sess = nullptr;
+    check(bp_ippx_begin_points(dev.ctx, G[0].data(), H[0].data(), G.size(), 1, Q.data(), pack(Gf).data(), pack(Hf).data(), pack(a).data(), pack(b).data(), &sess), dev.ctx, "bp_ippx_begin_points");
+    std::vector<Transcript *> ts = {&t};
+    try { InnerProductProof p = ipp_rounds_x(sess, dev.ctx, ts, a.size())[0]; bp_ippx_end(sess); return p; }
+    catch (...) { bp_ippx_end(sess); throw; }
+}
+// B proofs over the same generators G(n, m), H(n, m) in one device session (every MSM launch chain carries all proofs)
+std::vector<InnerProductProof> InnerProductProof::create_many(Device &dev, const BulletproofGens &gens, size_t n, size_t m, std::vector<Transcript *> &ts, const std::vector<CompressedRistretto> &Qs,
+                                                              const std::vector<std::vector<Scalar>> &Gfs, const std::vector<std::vector<Scalar>> &Hfs,
+                                                              const std::vector<std::vector<Scalar>> &as, const std::vector<std::vector<Scalar>> &bs) {
+    size_t B = ts.size(), N = n * m;
+    if (Qs.size() != B || Gfs.size() != B || Hfs.size() != B || as.size() != B || bs.size() != B || B == 0) throw std::invalid_argument("InnerProductProof::create_many: batch sizes differ");
+    std::vector<uint8_t> q(32 * B), gf(32 * B * N), hf(32 * B * N), av(32 * B * N), bv(32 * B * N);
+    parallel_for(B, [&](size_t p) {
+        ipp_check_lengths(N, Gfs[p], Hfs[p], as[p], bs[p]);
+        memcpy(q.data() + 32 * p, Qs[p].data(), 32);
+        memcpy(gf.data() + 32 * N * p, pack(Gfs[p]).data(), 32 * N); memcpy(hf.data() + 32 * N * p, pack(Hfs[p]).data(), 32 * N);
+        memcpy(av.data() + 32 * N * p, pack(as[p]).data(), 32 * N); memcpy(bv.data() + 32 * N * p, pack(bs[p]).data(), 32 * N);
+    });
+    bp_ippx *sess = nullptr;
+    check(bp_ippx_begin(dev.ctx, gens.handle, n, m, B, q.data(), gf.data(), hf.data(), av.data(), bv.data(), &sess), dev.ctx, "bp_ippx_begin");
+    try { std::vector<InnerProductProof> out = ipp_rounds_x(sess, dev.ctx, ts, N); bp_ippx_end(sess); return out; }
+    catch (...) { bp_ippx_end(sess); throw; }
 }
 
 ProofError InnerProductProof::verification_scalars(size_t n, Transcript &t, std::vector<Scalar> &u_sq, std::vector<Scalar> &u_inv_sq, std::vector<Scalar> &s) const {
@@ -281,100 +296,179 @@ Scalar scalar_exp_vartime(const Scalar &x, uint64_t n) {      // util.rs:222-234
     return result;
 }
 
+// Per-proof prover state between the batched device calls of prove_many
+namespace {
+struct ProverState {
+    size_t m = 0, N = 0; bool live = false;
+    std::vector<Scalar> a_bl, s_bl, sL, sR, l0, l1, r0, r1, t0, t1, t2, t1_bl, t2_bl, offset_zz, l_vec, r_vec, Gf, Hf;
+    Scalar y, z, zz, x, w;
+    CompressedRistretto Q;
+    size_t out_base = 0;        // first output slot of this proof in the current batched call
+};
+// the MSMs one proof asks for in a phase (scalars, table slots, end offsets), built per proof in parallel and merged into one device call
+struct MsmReq { std::vector<Scalar> sc; std::vector<uint32_t> idx; std::vector<uint64_t> off; };
+bool run_requests(Device &dev, const BulletproofGens &gens, const std::vector<MsmReq> &reqs, std::vector<ProverState> &st, std::vector<uint8_t> &out) {
+    size_t terms = 0, n_msm = 0;
+    for (const MsmReq &r : reqs) { terms += r.sc.size(); n_msm += r.off.size(); }
+    if (n_msm == 0) return false;
+    std::vector<uint8_t> sc(32 * terms); std::vector<uint32_t> idx(terms); std::vector<uint64_t> off(n_msm + 1); std::vector<size_t> base(reqs.size());
+    size_t t0 = 0, m0 = 0; off[0] = 0;
+    for (size_t p = 0; p < reqs.size(); p++) { base[p] = t0; st[p].out_base = m0; for (uint64_t e : reqs[p].off) off[++m0] = t0 + e; t0 += reqs[p].sc.size(); }
+    parallel_for(reqs.size(), [&](size_t p) {
+        for (size_t i = 0; i < reqs[p].sc.size(); i++) { reqs[p].sc[i].write(sc.data() + 32 * (base[p] + i)); idx[base[p] + i] = reqs[p].idx[i]; }
+    });
+    out.assign(32 * n_msm, 0); std::vector<uint8_t> stt(n_msm);
+    check(bp_msm_indexed_batch(dev.ctx, gens.handle, sc.data(), idx.data(), nullptr, 0, off.data(), n_msm, out.data(), stt.data()), dev.ctx, "bp_msm_indexed_batch");
+    return true;
+}
+}  // namespace
+
+// RangeProof::prove_multiple_with_rng (range_proof/mod.rs:234-288; the MPC run with itself, party.rs / dealer.rs) for a batch of proofs.
+// Each proof follows exactly the statement order of the single-proof flow (same transcript, same RNG draw order, App. A.2 of SURVEY.md);
+// only the device calls are shared: phase 1 = all V_j, A, S; phase 2 = all T_1, T_2; phase 3 = all Q = w B; phase 4 = all inner-product proofs.
+void RangeProof::prove_many(Device &dev, const BulletproofGens &gens, size_t n, std::vector<RangeProofJob> &jobs) {
+    const size_t B = jobs.size();
+    std::vector<ProverState> st(B);
+    const Scalar one = Scalar::one(), minus_one = -one;
+    // ---- phase 1: parameter checks, RNG draws, bit commitments
+    {
+        std::vector<MsmReq> reqs(B);
+        parallel_for(B, [&](size_t p) {
+            RangeProofJob &J = jobs[p]; ProverState &S = st[p];
+            std::vector<Scalar> &sc = reqs[p].sc; std::vector<uint32_t> &idx = reqs[p].idx; std::vector<uint64_t> &off = reqs[p].off;
+            size_t m = J.values.size();
+            if (m != J.blindings.size()) { J.error = ProofError::WrongNumBlindingFactors; return; }                   // mod.rs:246-248
+            if (!(n == 8 || n == 16 || n == 32 || n == 64)) { J.error = ProofError::InvalidBitsize; return; }       // dealer.rs:44-46
+            if (m == 0 || (m & (m - 1))) { J.error = ProofError::InvalidAggregation; return; }                      // dealer.rs:47-49
+            if (gens.gens_capacity < n || gens.party_capacity < m) { J.error = ProofError::InvalidGeneratorsLength; return; }   // dealer.rs:50-55
+            S.m = m; S.N = n * m; S.live = true;
+            J.t->rangeproof_domain_sep(n, m);                                                                          // dealer.rs:70
+            // RNG order per party: a_blinding, s_blinding, s_L[0..n), s_R[0..n)  (party.rs:98,114-116)
+            S.a_bl.resize(m); S.s_bl.resize(m); S.sL.resize(S.N); S.sR.resize(S.N);
+            for (size_t j = 0; j < m; j++) {
+                S.a_bl[j] = Scalar::random(*J.rng); S.s_bl[j] = Scalar::random(*J.rng);
+                for (size_t i = 0; i < n; i++) S.sL[j * n + i] = Scalar::random(*J.rng);
+                for (size_t i = 0; i < n; i++) S.sR[j * n + i] = Scalar::random(*J.rng);
+            }
+            // m + 2 constant-base MSMs: V_j = v_j B + v~_j B~ (party.rs:51), A = sum_j (a~_j B~ + sum_i [bit ? G : -H]) (party.rs:100-112,
+            // dealer.rs:112-113), S = sum_j (s~_j B~ + <s_L, G_j> + <s_R, H_j>) (party.rs:119-124, dealer.rs:115-116)
+            for (size_t j = 0; j < m; j++) { sc.push_back(Scalar::from_u64(J.values[j])); idx.push_back(gens.slot_B()); sc.push_back(J.blindings[j]); idx.push_back(gens.slot_B_blinding()); off.push_back(sc.size()); }
+            for (size_t j = 0; j < m; j++) {
+                sc.push_back(S.a_bl[j]); idx.push_back(gens.slot_B_blinding());
+                for (size_t i = 0; i < n; i++) { bool bit = (J.values[j] >> i) & 1; sc.push_back(bit ? one : minus_one); idx.push_back(bit ? gens.slot_G(j, i) : gens.slot_H(j, i)); }
+            }
+            off.push_back(sc.size());
+            for (size_t j = 0; j < m; j++) {
+                sc.push_back(S.s_bl[j]); idx.push_back(gens.slot_B_blinding());
+                for (size_t i = 0; i < n; i++) { sc.push_back(S.sL[j * n + i]); idx.push_back(gens.slot_G(j, i)); }
+                for (size_t i = 0; i < n; i++) { sc.push_back(S.sR[j * n + i]); idx.push_back(gens.slot_H(j, i)); }
+            }
+            off.push_back(sc.size());
+        });
+        std::vector<uint8_t> out;
+        if (!run_requests(dev, gens, reqs, st, out)) return;
+        for (size_t p = 0; p < B; p++) {
+            if (!st[p].live) continue;
+            RangeProofJob &J = jobs[p]; size_t m = st[p].m; const uint8_t *o = out.data() + 32 * st[p].out_base;
+            J.commitments.resize(m);
+            for (size_t j = 0; j < m; j++) memcpy(J.commitments[j].data(), o + 32 * j, 32);
+            memcpy(J.proof.A.data(), o + 32 * m, 32); memcpy(J.proof.S.data(), o + 32 * (m + 1), 32);
+        }
+    }
+    // ---- phase 2: bit challenge, polynomial commitments
+    {
+        std::vector<MsmReq> reqs(B);
+        parallel_for(B, [&](size_t p) {
+            if (!st[p].live) return;
+            RangeProofJob &J = jobs[p]; ProverState &S = st[p]; size_t m = S.m, N = S.N; Transcript &t = *J.t;
+            std::vector<Scalar> &sc = reqs[p].sc; std::vector<uint32_t> &idx = reqs[p].idx; std::vector<uint64_t> &off = reqs[p].off;
+            for (size_t j = 0; j < m; j++) t.append_point("V", J.commitments[j]);                        // dealer.rs:107-119
+            t.append_point("A", J.proof.A); t.append_point("S", J.proof.S);
+            S.y = t.challenge_scalar("y"); S.z = t.challenge_scalar("z"); S.zz = S.z * S.z;
+            // party.rs:182-237
+            S.l0.resize(N); S.l1.resize(N); S.r0.resize(N); S.r1.resize(N); S.t0.resize(m); S.t1.resize(m); S.t2.resize(m); S.t1_bl.resize(m); S.t2_bl.resize(m); S.offset_zz.resize(m);
+            for (size_t j = 0; j < m; j++) {
+                Scalar offset_y = scalar_exp_vartime(S.y, (uint64_t)(j * n)), offset_z = scalar_exp_vartime(S.z, (uint64_t)j);
+                S.offset_zz[j] = S.zz * offset_z;
+                Scalar exp_y = offset_y, exp_2 = Scalar::one();
+                for (size_t i = 0; i < n; i++) {
+                    size_t q = j * n + i;
+                    Scalar a_L = Scalar::from_u64((J.values[j] >> i) & 1), a_R = a_L - one;
+                    S.l0[q] = a_L - S.z; S.l1[q] = S.sL[q];
+                    S.r0[q] = exp_y * (a_R + S.z) + S.offset_zz[j] * exp_2; S.r1[q] = exp_y * S.sR[q];
+                    exp_y *= S.y; exp_2 = exp_2 + exp_2;
+                }
+                // VecPoly1::inner_product, Karatsuba (util.rs:86-100)
+                Scalar acc0 = Scalar::zero(), acc2 = Scalar::zero(), acc1 = Scalar::zero();
+                for (size_t i = 0; i < n; i++) { size_t q = j * n + i; acc0 += S.l0[q] * S.r0[q]; acc2 += S.l1[q] * S.r1[q]; acc1 += (S.l0[q] + S.l1[q]) * (S.r0[q] + S.r1[q]); }
+                S.t0[j] = acc0; S.t2[j] = acc2; S.t1[j] = acc1 - acc0 - acc2;
+            }
+            for (size_t j = 0; j < m; j++) { S.t1_bl[j] = Scalar::random(*J.rng); S.t2_bl[j] = Scalar::random(*J.rng); }      // party.rs:214-215, all parties in turn (mod.rs:272-275)
+            // T_1 = sum_j (t1_j B + t~1_j B~), T_2 likewise (party.rs:216-217, dealer.rs:169-170)
+            for (size_t j = 0; j < m; j++) { sc.push_back(S.t1[j]); idx.push_back(gens.slot_B()); sc.push_back(S.t1_bl[j]); idx.push_back(gens.slot_B_blinding()); }
+            off.push_back(sc.size());
+            for (size_t j = 0; j < m; j++) { sc.push_back(S.t2[j]); idx.push_back(gens.slot_B()); sc.push_back(S.t2_bl[j]); idx.push_back(gens.slot_B_blinding()); }
+            off.push_back(sc.size());
+        });
+        std::vector<uint8_t> out;
+        if (!run_requests(dev, gens, reqs, st, out)) return;
+        for (size_t p = 0; p < B; p++) {
+            if (!st[p].live) continue;
+            memcpy(jobs[p].proof.T_1.data(), out.data() + 32 * st[p].out_base, 32); memcpy(jobs[p].proof.T_2.data(), out.data() + 32 * (st[p].out_base + 1), 32);
+        }
+    }
+    // ---- phase 3: poly challenge, proof shares, Q = w B
+    {
+        std::vector<MsmReq> reqs(B);
+        parallel_for(B, [&](size_t p) {
+            if (!st[p].live) return;
+            RangeProofJob &J = jobs[p]; ProverState &S = st[p]; size_t m = S.m, N = S.N; Transcript &t = *J.t; RangeProof &proof = J.proof;
+            std::vector<Scalar> &sc = reqs[p].sc; std::vector<uint32_t> &idx = reqs[p].idx; std::vector<uint64_t> &off = reqs[p].off;
+            t.append_point("T_1", proof.T_1); t.append_point("T_2", proof.T_2);                          // dealer.rs:172-173
+            S.x = t.challenge_scalar("x");
+            if (S.x.is_zero()) { J.error = ProofError::MaliciousDealer; S.live = false; return; }        // party.rs:282-284
+            // party.rs:279-305, dealer.rs:245-270
+            proof.t_x = Scalar::zero(); proof.t_x_blinding = Scalar::zero(); proof.e_blinding = Scalar::zero();
+            S.l_vec.resize(N); S.r_vec.resize(N);
+            for (size_t j = 0; j < m; j++) {
+                proof.t_x += S.t0[j] + S.x * (S.t1[j] + S.x * S.t2[j]);
+                proof.t_x_blinding += S.offset_zz[j] * J.blindings[j] + S.x * (S.t1_bl[j] + S.x * S.t2_bl[j]);
+                proof.e_blinding += S.a_bl[j] + S.s_bl[j] * S.x;
+                for (size_t i = 0; i < n; i++) { size_t q = j * n + i; S.l_vec[q] = S.l0[q] + S.l1[q] * S.x; S.r_vec[q] = S.r0[q] + S.r1[q] * S.x; }
+            }
+            t.append_scalar("t_x", proof.t_x); t.append_scalar("t_x_blinding", proof.t_x_blinding); t.append_scalar("e_blinding", proof.e_blinding);
+            S.w = t.challenge_scalar("w");
+            sc.push_back(S.w); idx.push_back(gens.slot_B()); off.push_back(sc.size());                    // Q = w * B (dealer.rs:256)
+            S.Gf.assign(N, Scalar::one()); S.Hf.resize(N);
+            Scalar y_inv = S.y.invert(), e = Scalar::one();
+            for (size_t i = 0; i < N; i++) { S.Hf[i] = e; e *= y_inv; }                                   // dealer.rs:258-261
+        });
+        std::vector<uint8_t> out;
+        if (!run_requests(dev, gens, reqs, st, out)) return;
+        for (size_t p = 0; p < B; p++) if (st[p].live) memcpy(st[p].Q.data(), out.data() + 32 * st[p].out_base, 32);
+    }
+    // ---- phase 4: the inner-product arguments, grouped by aggregation size (one device session per distinct m)
+    for (size_t p0 = 0; p0 < B; p0++) {
+        if (!st[p0].live) continue;
+        size_t m = st[p0].m;
+        std::vector<size_t> who; std::vector<Transcript *> ts; std::vector<CompressedRistretto> Qs; std::vector<std::vector<Scalar>> Gfs, Hfs, as, bs;
+        for (size_t p = p0; p < B; p++)
+            if (st[p].live && st[p].m == m) {
+                who.push_back(p); ts.push_back(jobs[p].t); Qs.push_back(st[p].Q); Gfs.push_back(std::move(st[p].Gf)); Hfs.push_back(std::move(st[p].Hf));
+                as.push_back(std::move(st[p].l_vec)); bs.push_back(std::move(st[p].r_vec)); st[p].live = false;
+            }
+        std::vector<InnerProductProof> ipps = InnerProductProof::create_many(dev, gens, n, m, ts, Qs, Gfs, Hfs, as, bs);      // dealer.rs:272-281
+        for (size_t k = 0; k < who.size(); k++) jobs[who[k]].proof.ipp_proof = std::move(ipps[k]);
+    }
+}
+
 ProofError RangeProof::prove_multiple_with_rng(Device &dev, const BulletproofGens &gens, Transcript &t, const std::vector<uint64_t> &values,
                                                const std::vector<Scalar> &blindings, size_t n, Rng &rng, RangeProof &proof, std::vector<CompressedRistretto> &commitments) {
-    size_t m = values.size();
-    if (m != blindings.size()) return ProofError::WrongNumBlindingFactors;                               // mod.rs:246-248
-    if (!(n == 8 || n == 16 || n == 32 || n == 64)) return ProofError::InvalidBitsize;                   // dealer.rs:44-46
-    if (m == 0 || (m & (m - 1))) return ProofError::InvalidAggregation;                                  // dealer.rs:47-49
-    if (gens.gens_capacity < n || gens.party_capacity < m) return ProofError::InvalidGeneratorsLength;   // dealer.rs:50-55
-    size_t N = n * m;
-    t.rangeproof_domain_sep(n, m);                                                                       // dealer.rs:70
-
-    // --- parties: bit commitments.  RNG order per party: a_blinding, s_blinding, s_L[0..n), s_R[0..n)  (party.rs:98,114-116)
-    std::vector<Scalar> a_bl(m), s_bl(m), sL(N), sR(N);
-    for (size_t j = 0; j < m; j++) {
-        a_bl[j] = Scalar::random(rng); s_bl[j] = Scalar::random(rng);
-        for (size_t i = 0; i < n; i++) sL[j * n + i] = Scalar::random(rng);
-        for (size_t i = 0; i < n; i++) sR[j * n + i] = Scalar::random(rng);
-    }
-    // m + 2 constant-base MSMs in one call: V_j = v_j B + v~_j B~ (party.rs:51), A = sum_j (a~_j B~ + sum_i [bit ? G : -H]) (party.rs:100-112,
-    // dealer.rs:112-113), S = sum_j (s~_j B~ + <s_L, G_j> + <s_R, H_j>) (party.rs:119-124, dealer.rs:115-116)
-    std::vector<Scalar> sc1; std::vector<uint32_t> idx1; std::vector<uint64_t> off1 = {0};
-    Scalar one = Scalar::one(), minus_one = -one;
-    for (size_t j = 0; j < m; j++) { sc1.push_back(Scalar::from_u64(values[j])); idx1.push_back(gens.slot_B()); sc1.push_back(blindings[j]); idx1.push_back(gens.slot_B_blinding()); off1.push_back(sc1.size()); }
-    for (size_t j = 0; j < m; j++) {
-        sc1.push_back(a_bl[j]); idx1.push_back(gens.slot_B_blinding());
-        for (size_t i = 0; i < n; i++) { bool bit = (values[j] >> i) & 1; sc1.push_back(bit ? one : minus_one); idx1.push_back(bit ? gens.slot_G(j, i) : gens.slot_H(j, i)); }
-    }
-    off1.push_back(sc1.size());
-    for (size_t j = 0; j < m; j++) {
-        sc1.push_back(s_bl[j]); idx1.push_back(gens.slot_B_blinding());
-        for (size_t i = 0; i < n; i++) { sc1.push_back(sL[j * n + i]); idx1.push_back(gens.slot_G(j, i)); }
-        for (size_t i = 0; i < n; i++) { sc1.push_back(sR[j * n + i]); idx1.push_back(gens.slot_H(j, i)); }
-    }
-    off1.push_back(sc1.size());
-    std::vector<uint8_t> out1(32 * (m + 2)), st1(m + 2);
-    check(bp_msm_indexed_batch(dev.ctx, gens.handle, pack(sc1).data(), idx1.data(), nullptr, 0, off1.data(), m + 2, out1.data(), st1.data()), dev.ctx, "bp_msm_indexed_batch");
-    commitments.resize(m);
-    for (size_t j = 0; j < m; j++) memcpy(commitments[j].data(), out1.data() + 32 * j, 32);
-    memcpy(proof.A.data(), out1.data() + 32 * m, 32); memcpy(proof.S.data(), out1.data() + 32 * (m + 1), 32);
-
-    // --- dealer: bit challenge (dealer.rs:107-119)
-    for (size_t j = 0; j < m; j++) t.append_point("V", commitments[j]);
-    t.append_point("A", proof.A); t.append_point("S", proof.S);
-    Scalar y = t.challenge_scalar("y"), z = t.challenge_scalar("z"), zz = z * z;
-
-    // --- parties: polynomial commitments (party.rs:182-237)
-    std::vector<Scalar> l0(N), l1(N), r0(N), r1(N), t0(m), t1(m), t2(m), t1_bl(m), t2_bl(m), offset_zz(m);
-    for (size_t j = 0; j < m; j++) {
-        Scalar offset_y = scalar_exp_vartime(y, (uint64_t)(j * n)), offset_z = scalar_exp_vartime(z, (uint64_t)j);
-        offset_zz[j] = zz * offset_z;
-        Scalar exp_y = offset_y, exp_2 = Scalar::one();
-        for (size_t i = 0; i < n; i++) {
-            size_t q = j * n + i;
-            Scalar a_L = Scalar::from_u64((values[j] >> i) & 1), a_R = a_L - one;
-            l0[q] = a_L - z; l1[q] = sL[q];
-            r0[q] = exp_y * (a_R + z) + offset_zz[j] * exp_2; r1[q] = exp_y * sR[q];
-            exp_y *= y; exp_2 = exp_2 + exp_2;
-        }
-        // VecPoly1::inner_product, Karatsuba (util.rs:86-100)
-        Scalar acc0 = Scalar::zero(), acc2 = Scalar::zero(), acc1 = Scalar::zero();
-        for (size_t i = 0; i < n; i++) { size_t q = j * n + i; acc0 += l0[q] * r0[q]; acc2 += l1[q] * r1[q]; acc1 += (l0[q] + l1[q]) * (r0[q] + r1[q]); }
-        t0[j] = acc0; t2[j] = acc2; t1[j] = acc1 - acc0 - acc2;
-    }
-    for (size_t j = 0; j < m; j++) { t1_bl[j] = Scalar::random(rng); t2_bl[j] = Scalar::random(rng); }      // party.rs:214-215, all parties in turn (mod.rs:272-275)
-    // T_1 = sum_j (t1_j B + t~1_j B~), T_2 likewise (party.rs:216-217, dealer.rs:169-170): two MSMs in one call
-    std::vector<Scalar> sc2; std::vector<uint32_t> idx2; std::vector<uint64_t> off2 = {0};
-    for (size_t j = 0; j < m; j++) { sc2.push_back(t1[j]); idx2.push_back(gens.slot_B()); sc2.push_back(t1_bl[j]); idx2.push_back(gens.slot_B_blinding()); }
-    off2.push_back(sc2.size());
-    for (size_t j = 0; j < m; j++) { sc2.push_back(t2[j]); idx2.push_back(gens.slot_B()); sc2.push_back(t2_bl[j]); idx2.push_back(gens.slot_B_blinding()); }
-    off2.push_back(sc2.size());
-    uint8_t out2[64], st2[2];
-    check(bp_msm_indexed_batch(dev.ctx, gens.handle, pack(sc2).data(), idx2.data(), nullptr, 0, off2.data(), 2, out2, st2), dev.ctx, "bp_msm_indexed_batch");
-    memcpy(proof.T_1.data(), out2, 32); memcpy(proof.T_2.data(), out2 + 32, 32);
-    t.append_point("T_1", proof.T_1); t.append_point("T_2", proof.T_2);                                 // dealer.rs:172-173
-    Scalar x = t.challenge_scalar("x");
-    if (x.is_zero()) return ProofError::MaliciousDealer;                                                  // party.rs:282-284
-
-    // --- parties: proof shares; dealer: sums (party.rs:279-305, dealer.rs:245-270)
-    proof.t_x = Scalar::zero(); proof.t_x_blinding = Scalar::zero(); proof.e_blinding = Scalar::zero();
-    std::vector<Scalar> l_vec(N), r_vec(N);
-    for (size_t j = 0; j < m; j++) {
-        proof.t_x += t0[j] + x * (t1[j] + x * t2[j]);
-        proof.t_x_blinding += offset_zz[j] * blindings[j] + x * (t1_bl[j] + x * t2_bl[j]);
-        proof.e_blinding += a_bl[j] + s_bl[j] * x;
-        for (size_t i = 0; i < n; i++) { size_t q = j * n + i; l_vec[q] = l0[q] + l1[q] * x; r_vec[q] = r0[q] + r1[q] * x; }
-    }
-    t.append_scalar("t_x", proof.t_x); t.append_scalar("t_x_blinding", proof.t_x_blinding); t.append_scalar("e_blinding", proof.e_blinding);
-    Scalar w = t.challenge_scalar("w");
-    // Q = w * B (dealer.rs:256)
-    CompressedRistretto Q; uint32_t qi = gens.slot_B(); uint64_t qo[2] = {0, 1}; uint8_t qs;
-    check(bp_msm_indexed_batch(dev.ctx, gens.handle, w.to_bytes().data(), &qi, nullptr, 0, qo, 1, Q.data(), &qs), dev.ctx, "bp_msm_indexed_batch");
-    std::vector<Scalar> Gf(N, Scalar::one()), Hf(N);
-    Scalar y_inv = y.invert(), e = Scalar::one();
-    for (size_t i = 0; i < N; i++) { Hf[i] = e; e *= y_inv; }                                            // dealer.rs:258-261
-    proof.ipp_proof = InnerProductProof::create(dev, gens, n, m, t, Q, Gf, Hf, std::move(l_vec), std::move(r_vec));
+    std::vector<RangeProofJob> jobs(1);
+    jobs[0].t = &t; jobs[0].values = values; jobs[0].blindings = blindings; jobs[0].rng = &rng;
+    prove_many(dev, gens, n, jobs);
+    if (jobs[0].error != ProofError::Ok) return jobs[0].error;
+    proof = std::move(jobs[0].proof); commitments = std::move(jobs[0].commitments);
     return ProofError::Ok;
 }
 
@@ -423,6 +517,32 @@ int bph_rangeproof_prove(bp_ctx *ctx, bp_gens *gens, size_t gens_capacity, size_
         memcpy(proof_out, bytes.data(), bytes.size());
         for (size_t j = 0; j < m; j++) memcpy(commitments_out + 32 * j, V[j].data(), 32);
         t.to_wire(transcript);
+        return 0;
+    } catch (const std::exception &) { return -1; }
+}
+// B proofs with m values each, every group operation batched across the proofs: transcripts all start from `transcript`, proof p uses
+// ChaChaRng::from_seed(rng_seeds[p]); status_out[p] = ProofError code
+int bph_rangeproof_prove_many(bp_ctx *ctx, bp_gens *gens, size_t gens_capacity, size_t party_capacity, const uint8_t *transcript, const uint64_t *values, const uint8_t *blindings,
+                              size_t m, size_t n, size_t count, const uint8_t *rng_seeds, uint8_t *proofs_out, size_t proof_len, uint8_t *commitments_out, uint8_t *status_out) {
+    try {
+        Device dev(ctx); BulletproofGens g{gens, gens_capacity, party_capacity};
+        std::vector<Transcript> ts(count, Transcript(transcript)); std::vector<ChaChaRng> rngs; rngs.reserve(count);
+        std::vector<RangeProofJob> jobs(count);
+        for (size_t p = 0; p < count; p++) {
+            rngs.emplace_back(rng_seeds + 32 * p);
+            jobs[p].t = &ts[p]; jobs[p].rng = &rngs[p];
+            jobs[p].values.assign(values + p * m, values + (p + 1) * m); jobs[p].blindings.resize(m);
+            for (size_t j = 0; j < m; j++) if (!Scalar::from_canonical_bytes(blindings + 32 * (p * m + j), jobs[p].blindings[j])) return -3;
+        }
+        RangeProof::prove_many(dev, g, n, jobs);
+        for (size_t p = 0; p < count; p++) {
+            status_out[p] = (uint8_t)jobs[p].error;
+            if (jobs[p].error != ProofError::Ok) continue;
+            std::vector<uint8_t> bytes = jobs[p].proof.to_bytes();
+            if (bytes.size() != proof_len) return -4;
+            memcpy(proofs_out + p * proof_len, bytes.data(), proof_len);
+            for (size_t j = 0; j < m; j++) memcpy(commitments_out + 32 * (p * m + j), jobs[p].commitments[j].data(), 32);
+        }
         return 0;
     } catch (const std::exception &) { return -1; }
 }

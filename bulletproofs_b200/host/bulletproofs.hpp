@@ -10,6 +10,10 @@
 //   bulletproofs::InnerProductProof::{create, verify, to_bytes, from_bytes}   (/root/reference/src/inner_product_proof.rs:38-407)
 //   bulletproofs::RangeProof::{prove_multiple_with_rng, verify_multiple, to_bytes, from_bytes}  (/root/reference/src/range_proof/mod.rs:234-538)
 #pragma once
+#include <atomic>
+#include <exception>
+#include <thread>
+#include <sched.h>
 #include <array>
 #include <cstdint>
 #include <cstring>
@@ -62,6 +66,24 @@ public:
     bool is_zero() const { return sc_is_zero(m_); }
     Scalar invert() const { return Scalar(sc_mont_invert(m_)); }     // 0 -> 0, like dalek
 };
+// Host-side work of a batch (transcripts, scalar vectors, RNG draws) is independent per proof: spread it over the cores this process may use.
+// Device calls stay on the calling thread.
+template <class F> inline void parallel_for(size_t n, F fn) {
+    cpu_set_t set; CPU_ZERO(&set);
+    size_t cores = sched_getaffinity(0, sizeof set, &set) == 0 ? (size_t)CPU_COUNT(&set) : 1;
+    size_t nt = std::min<size_t>(std::max<size_t>(cores, 1), n);
+    if (nt <= 1) { for (size_t i = 0; i < n; i++) fn(i); return; }
+    std::atomic<size_t> next{0}; std::exception_ptr err; std::atomic<bool> failed{false};
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < nt; t++)
+        th.emplace_back([&] {
+            try { for (size_t i; (i = next++) < n;) fn(i); }
+            catch (...) { if (!failed.exchange(true)) err = std::current_exception(); }
+        });
+    for (auto &x : th) x.join();
+    if (failed) std::rethrow_exception(err);
+}
+
 Scalar inner_product(const std::vector<Scalar> &a, const std::vector<Scalar> &b);     // inner_product_proof.rs:418-427
 Scalar scalar_exp_vartime(const Scalar &x, uint64_t n);                               // util.rs:222-234
 
@@ -113,6 +135,10 @@ struct InnerProductProof {
     // create over arbitrary vectors (inner_product_proof.rs:38-47)
     static InnerProductProof create(Device &dev, Transcript &t, const CompressedRistretto &Q, const std::vector<Scalar> &G_factors, const std::vector<Scalar> &H_factors,
                                     const std::vector<CompressedRistretto> &G, const std::vector<CompressedRistretto> &H, std::vector<Scalar> a, std::vector<Scalar> b);
+    // B independent proofs over the same generators, all MSM launch chains shared (batched prover)
+    static std::vector<InnerProductProof> create_many(Device &dev, const BulletproofGens &gens, size_t n, size_t m, std::vector<Transcript *> &ts, const std::vector<CompressedRistretto> &Qs,
+                                                      const std::vector<std::vector<Scalar>> &G_factors, const std::vector<std::vector<Scalar>> &H_factors,
+                                                      const std::vector<std::vector<Scalar>> &as, const std::vector<std::vector<Scalar>> &bs);
     // verification_scalars (inner_product_proof.rs:198-253)
     ProofError verification_scalars(size_t n, Transcript &t, std::vector<Scalar> &u_sq, std::vector<Scalar> &u_inv_sq, std::vector<Scalar> &s) const;
     // verify (inner_product_proof.rs:260-326)
@@ -138,10 +164,17 @@ struct RangeProof {
     // range_proof/mod.rs:234-288 (the MPC run with itself: party.rs / dealer.rs)
     static ProofError prove_multiple_with_rng(Device &dev, const BulletproofGens &gens, Transcript &t, const std::vector<uint64_t> &values,
                                               const std::vector<Scalar> &blindings, size_t n, Rng &rng, RangeProof &proof, std::vector<CompressedRistretto> &commitments);
+    // B independent aggregated proofs (same n, same number of values m each) with every group operation batched across the proofs:
+    // one call for all V/A/S commitments, one for all T_1/T_2, one for all Q, one device session for all inner-product arguments.
+    // Same bytes as B calls of prove_multiple_with_rng with the same transcripts and RNGs.
+    static void prove_many(Device &dev, const BulletproofGens &gens, size_t n, std::vector<struct RangeProofJob> &jobs);
     // range_proof/mod.rs:345-452 through the batch verifier with count = 1
     ProofError verify_multiple(Device &dev, const BulletproofGens &gens, const Transcript &t, const std::vector<CompressedRistretto> &commitments, size_t n) const;
     std::vector<uint8_t> to_bytes() const;                                         // mod.rs:487-499
     static ProofError from_bytes(const uint8_t *s, size_t len, RangeProof &out);   // mod.rs:505-538
 };
+
+// one proof of a RangeProof::prove_many batch: inputs (transcript, values, blindings, rng) and outputs (proof, commitments, error)
+struct RangeProofJob { Transcript *t; std::vector<uint64_t> values; std::vector<Scalar> blindings; Rng *rng; RangeProof proof; std::vector<CompressedRistretto> commitments; ProofError error = ProofError::Ok; };
 
 }  // namespace bulletproofs

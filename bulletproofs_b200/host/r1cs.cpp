@@ -7,7 +7,12 @@ namespace r1cs {
 static void check(int rc, bp_ctx *ctx, const char *what) {
     if (rc != BP_OK) throw std::runtime_error(std::string(what) + " failed with code " + std::to_string(rc) + ": " + bp_last_error(ctx));
 }
-static std::vector<uint8_t> pack(const std::vector<Scalar> &v) { std::vector<uint8_t> o(32 * v.size()); for (size_t i = 0; i < v.size(); i++) v[i].write(o.data() + 32 * i); return o; }
+static std::vector<uint8_t> pack(const std::vector<Scalar> &v) {
+    std::vector<uint8_t> o(32 * v.size());
+    const size_t CH = 8192, nch = (v.size() + CH - 1) / CH;
+    parallel_for(nch, [&](size_t c) { for (size_t i = c * CH; i < std::min(v.size(), (c + 1) * CH); i++) v[i].write(o.data() + 32 * i); });
+    return o;
+}
 static size_t next_pow2(size_t n) { size_t p = 1; while (p < n) p <<= 1; return p; }
 static bool is_identity(const CompressedRistretto &p) { uint8_t z = 0; for (uint8_t b : p) z |= b; return z == 0; }
 
@@ -207,12 +212,19 @@ R1CSError Prover::prove(Rng &external_rng, R1CSProof &proof) {
     // l(x), r(x) (prover.rs:547-573) and t(x) = <l, r> (util.rs:125-142)
     std::vector<Scalar> l1(n), l2(n), l3(n), r0(n), r1(n), r3(n), exp_y_inv(padded_n);
     Scalar y_inv = y.invert(), exp_y = Scalar::one();
-    { Scalar e = Scalar::one(); for (size_t i = 0; i < padded_n; i++) { exp_y_inv[i] = e; e *= y_inv; } }
-    for (size_t i = 0; i < n; i++) {
-        l1[i] = a_L_[i] + exp_y_inv[i] * wR[i]; l2[i] = a_O_[i]; l3[i] = s_L[i];
-        r0[i] = wO[i] - exp_y; r1[i] = exp_y * a_R_[i] + wL[i]; r3[i] = exp_y * s_R[i];
-        exp_y *= y;
-    }
+    // powers of y and y^-1 and the six coefficient vectors, chunked over the host cores (each chunk starts from its own power)
+    const size_t CH = 4096, nch = (padded_n + CH - 1) / CH;
+    std::vector<Scalar> exp_y_pow(padded_n);
+    parallel_for(nch, [&](size_t c) {
+        size_t lo = c * CH, hi = std::min(padded_n, lo + CH);
+        Scalar e = scalar_exp_vartime(y_inv, (uint64_t)lo), f = scalar_exp_vartime(y, (uint64_t)lo);
+        for (size_t i = lo; i < hi; i++) { exp_y_inv[i] = e; e *= y_inv; exp_y_pow[i] = f; f *= y; }
+        for (size_t i = lo; i < std::min(hi, n); i++) {
+            l1[i] = a_L_[i] + exp_y_inv[i] * wR[i]; l2[i] = a_O_[i]; l3[i] = s_L[i];
+            r0[i] = wO[i] - exp_y_pow[i]; r1[i] = exp_y_pow[i] * a_R_[i] + wL[i]; r3[i] = exp_y_pow[i] * s_R[i];
+        }
+    });
+    (void)exp_y;
     Scalar t1 = inner_product(l1, r0), t2 = inner_product(l1, r1) + inner_product(l2, r0), t3 = inner_product(l2, r1) + inner_product(l3, r0),
            t4 = inner_product(l1, r3) + inner_product(l3, r1), t5 = inner_product(l2, r3), t6 = inner_product(l3, r3);
     Scalar t1b = Scalar::random(rng), t3b = Scalar::random(rng), t4b = Scalar::random(rng), t5b = Scalar::random(rng), t6b = Scalar::random(rng);
@@ -231,8 +243,13 @@ R1CSError Prover::prove(Rng &external_rng, R1CSProof &proof) {
     proof.t_x = x * (t1 + x * (t2 + x * (t3 + x * (t4 + x * (t5 + x * t6)))));            // Poly6::eval (util.rs:164-168)
     proof.t_x_blinding = x * (t1b + x * (t2b + x * (t3b + x * (t4b + x * (t5b + x * t6b)))));
     std::vector<Scalar> l_vec(padded_n), r_vec(padded_n);
-    for (size_t i = 0; i < n; i++) { l_vec[i] = x * (l1[i] + x * (l2[i] + x * l3[i])); r_vec[i] = r0[i] + x * (r1[i] + x * (x * r3[i])); }
-    for (size_t i = n; i < padded_n; i++) { r_vec[i] = -exp_y; exp_y *= y; }
+    parallel_for(nch, [&](size_t c) {
+        size_t lo = c * CH, hi = std::min(padded_n, lo + CH);
+        for (size_t i = lo; i < hi; i++) {
+            if (i < n) { l_vec[i] = x * (l1[i] + x * (l2[i] + x * l3[i])); r_vec[i] = r0[i] + x * (r1[i] + x * (x * r3[i])); }
+            else r_vec[i] = -exp_y_pow[i];
+        }
+    });
     Scalar i_bl = i_bl1 + u * i_bl2, o_bl = o_bl1 + u * o_bl2, s_bl = s_bl1 + u * s_bl2;
     proof.e_blinding = x * (i_bl + x * (o_bl + x * s_bl));
     t_.append_scalar("t_x", proof.t_x); t_.append_scalar("t_x_blinding", proof.t_x_blinding); t_.append_scalar("e_blinding", proof.e_blinding);
@@ -240,7 +257,9 @@ R1CSError Prover::prove(Rng &external_rng, R1CSProof &proof) {
     CompressedRistretto Q; uint32_t qi = gens_.slot_B(); uint64_t qo[2] = {0, 1}; uint8_t qs;
     check(bp_msm_indexed_batch(dev_.ctx, gens_.handle, w.to_bytes().data(), &qi, nullptr, 0, qo, 1, Q.data(), &qs), dev_.ctx, "Q");
     std::vector<Scalar> Gf(padded_n), Hf(padded_n);
-    for (size_t i = 0; i < padded_n; i++) { Gf[i] = i < n1 ? Scalar::one() : u; Hf[i] = exp_y_inv[i] * Gf[i]; }      // prover.rs:648-656
+    parallel_for(nch, [&](size_t c) {                                                                                 // prover.rs:648-656
+        for (size_t i = c * CH; i < std::min(padded_n, (c + 1) * CH); i++) { Gf[i] = i < n1 ? Scalar::one() : u; Hf[i] = exp_y_inv[i] * Gf[i]; }
+    });
     proof.ipp_proof = InnerProductProof::create(dev_, gens_, padded_n, 1, t_, Q, Gf, Hf, std::move(l_vec), std::move(r_vec));
     return R1CSError::Ok;
 }

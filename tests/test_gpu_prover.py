@@ -101,3 +101,63 @@ def test_indexed_msm_uses_the_resident_table(gpu_ctx, orc):
     pts = orc.gens_get(og, 0, 1, 3) + orc.gens_get(og, 1, 0, 7) + dyn[0] + dyn[2] + B
     assert (0, outs.raw[32:]) == orc.msm(b"".join(le(x) for x in s), pts)
     gens.close()
+
+
+@pytest.mark.parametrize("n,m,count", [(32, 1, 1), (32, 1, 9), (64, 1, 16), (8, 2, 5), (64, 4, 3)])
+def test_batched_prover_bytes_match_oracle(gpu_ctx, orc, n, m, count):
+    """RangeProof::prove_many: B proofs with every group operation batched across the proofs (one device session for all inner-product
+    arguments, generators never folded) must give exactly the bytes of B independent reference provers (oracle prove_many)."""
+    import bulletproofs_b200 as bp
+    gens = bp.Gens(gpu_ctx, 64, 4); og = orc.gens(64, 4)
+    rnd = random.Random(1000 * n + 10 * m + count)
+    label = b"AggregateRangeProofBenchmark"
+    values = [rnd.randrange(1 << n) for _ in range(count * m)]
+    blind = b"".join(le(rnd.randrange(l)) for _ in range(count * m))
+    seeds = b"".join(le(1000 + i, 8) + bytes(24) for i in range(count))
+    st, proofs, V = bp.prove_many(gpu_ctx, gens, bp.Transcript(label), values, blind, n, m, seeds)
+    want_proofs, want_V = orc.prove_many(og, orc.transcript(label), values, blind, n, m, seeds, nthreads=4)
+    assert st == [0] * count and V == want_V
+    plen = len(want_proofs) // count
+    for i in range(count):
+        assert proofs[i * plen:(i + 1) * plen] == want_proofs[i * plen:(i + 1) * plen], i
+    assert bp.verify_batch(gpu_ctx, gens, bp.Transcript(label), proofs, V, n, m, count) == [0] * count
+    gens.close()
+
+
+def test_unfolded_ipp_session_rounds(gpu_ctx, orc):
+    """bp_ippx_*: the device-resident inner-product prover state (no generator folding) round by round through the C ABI, two proofs side
+    by side over arbitrary points; L, R, a, b == the oracle's InnerProductProof::create bytes."""
+    import ctypes
+    import bulletproofs_b200 as bp
+    L = bp.lib(); rnd = random.Random(77)
+    N, B = 16, 2
+    G = b"".join(orc.from_uniform(rnd.randbytes(64)) for _ in range(N)); H = b"".join(orc.from_uniform(rnd.randbytes(64)) for _ in range(N))
+    Q = [orc.from_uniform(rnd.randbytes(64)) for _ in range(B)]
+    Gf = [b"".join(le(rnd.randrange(l)) for _ in range(N)) for _ in range(B)]; Hf = [b"".join(le(rnd.randrange(l)) for _ in range(N)) for _ in range(B)]
+    a = [b"".join(le(rnd.randrange(l)) for _ in range(N)) for _ in range(B)]; b = [b"".join(le(rnd.randrange(l)) for _ in range(N)) for _ in range(B)]
+    want = [orc.ipp_create(orc.transcript(b"ipp x"), Q[p], Gf[p], Hf[p], G, H, a[p], b[p], N)[2] for p in range(B)]
+    sess = ctypes.c_void_p()
+    gpu_ctx._check(L.bp_ippx_begin_points(gpu_ctx._h, G, H, N, B, b"".join(Q), b"".join(Gf), b"".join(Hf), b"".join(a), b"".join(b), ctypes.byref(sess)))
+    ts = [bp.Transcript(b"ipp x") for _ in range(B)]
+    for t in ts:
+        t.append_message(b"dom-sep", b"ipp v1"); t.append_u64(b"n", N)
+    got = [b"" for _ in range(B)]
+    n = N
+    while n > 1:
+        assert L.bp_ippx_current_len(sess) == n
+        lr = ctypes.create_string_buffer(64 * B)
+        gpu_ctx._check(L.bp_ippx_round(sess, lr))
+        us, uis = b"", b""
+        for p in range(B):
+            Lp, Rp = lr.raw[64 * p:64 * p + 32], lr.raw[64 * p + 32:64 * p + 64]
+            got[p] += Lp + Rp
+            ts[p].append_message(b"L", Lp); ts[p].append_message(b"R", Rp)
+            u = int.from_bytes(ts[p].challenge_bytes(b"u", 64), "little") % l
+            us += le(u); uis += le(pow(u, l - 2, l))
+        gpu_ctx._check(L.bp_ippx_fold(sess, us, uis))
+        n //= 2
+    ab = ctypes.create_string_buffer(64 * B)
+    gpu_ctx._check(L.bp_ippx_finish(sess, ab))
+    L.bp_ippx_end(sess)
+    for p in range(B):
+        assert got[p] + ab.raw[64 * p:64 * p + 64] == want[p], p

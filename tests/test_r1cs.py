@@ -64,7 +64,7 @@ def test_oracle_shuffle(orc, k):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("k", [1, 2, 5, 8, 42, 300])
+@pytest.mark.parametrize("k", [1, 2, 5, 8, 42, 300, 2049])        # 2049 inputs = 4096 multipliers: R1CSProof bytes still equal the oracle's
 def test_gpu_shuffle_matches_oracle(gpu_ctx, orc, k):
     import bulletproofs_b200 as bp
     cap = max(128, 1 << (2 * k).bit_length())

@@ -242,7 +242,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--streams", type=int, default=4, help="launch groups in flight (one context + stream each)")
+    ap.add_argument("--streams", type=int, default=8, help="launch groups in flight (one context + stream each)")
     ap.add_argument("--group", type=int, default=8, help="batches per launch group")
     ap.add_argument("--threads", type=int, default=0, help="host threads issuing groups; 0 = min(2, host cores per rank)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -251,6 +251,7 @@ def main():
     ap.add_argument("--workload", default="rangeproof", choices=["rangeproof", "msm"])
     ap.add_argument("--lg", type=int, default=16, help="--workload msm: terms per MSM = 2^lg")
     ap.add_argument("--msms", type=int, default=8, help="--workload msm: MSMs per call")
+    ap.add_argument("--window", type=int, default=0, help="--workload msm: fix the Pippenger window (bits); 0 = by size")
     ap.add_argument("--check-lg", type=int, default=16, help="--workload msm: compare the first MSM with the CPU oracle up to this size")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -79,6 +79,8 @@ def main(args, rank, world, local, local_world):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     stream = torch.cuda.Stream(device=local)
     ctx = bp.Context(local, stream=stream.cuda_stream)
+    if getattr(args, "window", 0):
+        ctx.set_msm_window(args.window)
     points = ctx.from_uniform_bytes(g_chain_uniform(n))                      # n x 32 B compressed, derived on the GPU
     # scalar pool: at least one call's worth, and more than L2
     T = M * n
@@ -177,7 +179,7 @@ def main(args, rank, world, local, local_world):
         pass
     peak = peaks.get("hbm_gbs", 6650.0)
     alg = M * (64 * n + 32)
-    cwin = {10: 8, 11: 8, 12: 9, 13: 10, 14: 10, 15: 11, 16: 12, 17: 12, 18: 13, 19: 14, 20: 14}.get(args.lg, 12)
+    cwin = getattr(args, "window", 0) or {10: 8, 11: 8, 12: 10, 13: 10, 14: 11, 15: 11, 16: 13, 17: 13, 18: 13, 19: 15, 20: 15}.get(args.lg, 13)
     W = (255 + cwin - 1) // cwin
     wide = T * W * 7 * 72 + M * W * (1 << (cwin - 1)) * 3 * 9 * 72
     roofline = {"bound": "hbm", "kernel": dom, "achieved": alg / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None,

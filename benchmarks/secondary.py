@@ -2,9 +2,8 @@
   config 1  (32,1) prove + verify latency, GPU-backed path vs the CPU oracle, proof bytes compared
   config 2  reject path: the 1024-proof batch with one corrupted proof (RLC fails -> per-proof recheck)
   config 3  256 x (64,16) aggregated proofs, single blocking call (the pipelined figure is `bench.py --m 16 --batch 256`)
-  config 4  Ristretto MSM sweep n = 2^10 .. 2^20: points = first n outputs of the party-0 'G' generator chain,
-            scalars = ChaCha20(seed 0x2a x 32) 64 B wide-reduced; 8 MSMs per call through bp_msm_batch (host buffers,
-            decompression included); every first result compared byte-for-byte with the CPU oracle.
+  config 4  Ristretto MSM sweep (pageable host buffers through bp_msm_batch, decompression included; every first result compared
+            byte-for-byte with the CPU oracle).  The measured sweep of record is `bench.py --workload msm` (profiles/r2_msm_sweep.md).
 Prints one JSON object."""
 import hashlib, json, os, random, statistics, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -56,7 +55,7 @@ assert got == [0] * 517 + [1] + [0] * (count - 518)
 res["config2_reject_path"] = {
     "accept_single_call_ms": round(1e3 * med(lambda: bp.verify_batch(ctx, gens, t, proofs, Vs, n, m, count), 10), 3),
     "one_bad_proof_single_call_ms": round(1e3 * med(lambda: bp.verify_batch(ctx, gens, t, bad, Vs, n, m, count), 10), 3),
-    "note": "blocking bp_rangeproof_verify_batch with host buffers, one stream; on an RLC failure every proof is rechecked by its own MSM (1024 MSMs of 147 terms in one launch chain)"}
+    "note": "blocking bp_rangeproof_verify_batch with host buffers, one stream; on an RLC failure the batch is rechecked in two levels: 32 chunk MSMs, then the 32 proofs of the failing chunk (benchmarks/reject_path.py has more cases)"}
 gens.close()
 
 # ---- config 3: 256 x (64,16)

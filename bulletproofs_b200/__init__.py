@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("BPMSM_LIB_EXPERIMENT") or os.path.join(_HERE, "libbpmsm.so")     # the override exists for A/B builds of the same source (benchmarks/)
+LIB_PATH = os.path.join(_HERE, "libbpmsm.so")
 
 TRANSCRIPT_BYTES = 203
 OK, ERR_INVALID_POINT, ERR_LENGTH_MISMATCH, ERR_NONCANONICAL_SCALAR, ERR_CUDA, ERR_INVALID_ARGUMENT = range(6)
@@ -24,6 +24,7 @@ SYMBOLS = {
     "bp_last_error": (_c.c_char_p, [_vp]),
     "bp_ctx_launch_count": (_c.c_uint64, [_vp]),
     "bp_ctx_synchronize": (_int, [_vp]),
+    "bp_ctx_set_msm_window": (_int, [_vp, _int]),
     "bp_decompress_check_batch": (_int, [_vp, _u8p, _sz, _u8p]),
     "bp_from_uniform_bytes_batch": (_int, [_vp, _u8p, _sz, _u8p]),
     "bp_decompress_batch": (_int, [_vp, _u8p, _sz, _u8p, _u8p]),
@@ -227,6 +228,10 @@ class Context:
 
     def synchronize(self):
         self._check(lib().bp_ctx_synchronize(self._h))
+
+    def set_msm_window(self, bits: int):
+        """Pippenger window of the generic MSM entry points: 0 = by size (default), 2..18 = fixed"""
+        self._check(lib().bp_ctx_set_msm_window(self._h, bits))
 
     def prof_enable(self, on=True):
         self._check(lib().bp_prof_enable(self._h, 1 if on else 0))

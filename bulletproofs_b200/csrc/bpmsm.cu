@@ -50,6 +50,7 @@ struct bp_ctx {
     int device = 0, sm_count = 148; cudaStream_t stream = nullptr; bool own_stream = false;
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;    // second branch of the verifier's launch graph
     std::string err; uint64_t launches = 0;
+    int msm_window = 0;                                       // 0 = by size (msm_pick_window); bp_ctx_set_msm_window pins it (tuning / tests)
     bool prof_on = false; std::vector<ProfRec> prof;          // per-kernel CUDA-event timing (bp_prof_*)
     // MSM scratch
     DevBuf in_scalars, in_points, in_offsets, niels, ok, msm_err, results, outs, flags, ix_pidx;
@@ -58,7 +59,7 @@ struct bp_ctx {
     // regrow -- i.e. move -- a buffer whose address is baked into the captured graph.
     MsmArena ar_rp;
     DevBuf rp_niels, rp_results;
-    DevBuf rp_chal, rp_raw, rp_work, rp_tabs, pow2_tab, rp_proofs, rp_commit, rp_par, rp_contrib, rp_part, rp_scalars, rp_status, rp_decbad, rp_pidx, rp_offsets, rp_verdict, rp_batch_ok, rp_combined;
+    DevBuf rp_chal, rp_raw, rp_tabs, pow2_tab, rp_proofs, rp_commit, rp_par, rp_contrib, rp_part, rp_scalars, rp_status, rp_decbad, rp_pidx, rp_offsets, rp_verdict, rp_batch_ok, rp_combined;
     DevBuf fb_scalars, fb_pidx, fb_offsets;
     uint32_t *h_verdict = nullptr; size_t h_verdict_cap = 0;       // pinned
     uint32_t *h_flag = nullptr;                                      // pinned: combined_ok[BP_MAX_GROUP_BATCHES] | batch_ok[BP_MAX_GROUP_BATCHES]
@@ -160,7 +161,9 @@ int msm_launch(bp_ctx *ctx, MsmArena &ar, const MsmArgs &a, const MsmPlan &p, ge
         a.d_offsets, ar.order.as<uint32_t>(), W, nb, n_buckets, a.d_point_idx, a.d_static, a.d_dynamic, ar.buckets.as<ge_ext>(), heavy_min, light_, heavy_n, heavy)); } while (0)
     if (acc_split == 2) ACC_LAUNCH(2); else ACC_LAUNCH(1);
 #undef ACC_LAUNCH
-    unsigned rthreads = nb >= 64 ? 64 : 32;      // two warps per segment: fewer scan/tree additions per useful bucket addition
+    // two warps per segment up to 2048 buckets (fewer scan / tree additions per useful bucket addition); eight for the wide windows of
+    // large MSMs, where a segment's 16k-32k buckets would otherwise be 256-512 sequential additions per thread
+    unsigned rthreads = nb >= 4096 ? 256 : nb >= 64 ? 64 : 32;
     LAUNCH(ctx, KID_MSM_REDUCE, k_msm_reduce<<<(unsigned)segs, rthreads, 0, s>>>(ar.buckets.as<ge_ext>(), nb, ar.wsums.as<ge_ext>()));
     if (a.n_msm <= 256)      // few MSMs: the Horner chain is pure latency -> four cooperating lanes per MSM
         LAUNCH(ctx, KID_MSM_COMBINE, k_msm_combine4<<<blocks_for(a.n_msm, 8), 32, 0, s>>>(ar.wsums.as<ge_ext>(), a.n_msm, c, W, d_results));
@@ -170,7 +173,7 @@ int msm_launch(bp_ctx *ctx, MsmArena &ar, const MsmArgs &a, const MsmPlan &p, ge
 }
 int msm_core(bp_ctx *ctx, const MsmArgs &a, ge_ext *d_results) {       // generic arena
     if (a.T == 0) return BP_ERR_INVALID_ARGUMENT;
-    MsmPlan p = msm_make_plan(a.T, a.n_msm, a.window);
+    MsmPlan p = msm_make_plan(a.T, a.n_msm, a.window > 0 ? a.window : ctx->msm_window);
     int rc = msm_ensure(ctx, ctx->ar_gen, p);
     if (rc) return rc;
     return msm_launch(ctx, ctx->ar_gen, a, p, d_results);
@@ -257,8 +260,7 @@ int bp_ctx_create(int device, void *stream, bp_ctx **out) {
     if (cudaMallocHost((void **)&c->h_stage, 512 * bp_ctx::STAGE_SLOTS) != cudaSuccess) { cudaFreeHost(c->h_flag); delete c; return BP_ERR_CUDA; }
     for (int i = 0; i < bp_ctx::STAGE_SLOTS; i++) cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming);
     cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking);
-    // the per-proof kernels stage their block's proofs in dynamic shared memory: up to 32 proofs of 32*(9+2*20) + 32*m bytes
-    cudaFuncSetAttribute(k_rp_transcript, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    // k_rp_decompress stages the proofs its block touches in dynamic shared memory: up to 13 proofs of 32*(9+2*20) + 32*m bytes
     cudaFuncSetAttribute(k_rp_decompress, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming);
     *out = c;
@@ -270,7 +272,7 @@ void bp_ctx_destroy(bp_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->aux) cudaStreamSynchronize(c->aux);
     if (c->graph) cudaGraphExecDestroy(c->graph);
-    DevBuf *bufs[] = {&c->in_scalars, &c->in_points, &c->in_offsets, &c->niels, &c->ok, &c->msm_err, &c->results, &c->outs, &c->flags, &c->ix_pidx, &c->rp_niels, &c->rp_results, &c->rp_chal, &c->rp_raw, &c->rp_work, &c->rp_tabs, &c->pow2_tab, &c->rp_proofs, &c->rp_commit, &c->rp_par, &c->rp_contrib, &c->rp_part, &c->rp_scalars,
+    DevBuf *bufs[] = {&c->in_scalars, &c->in_points, &c->in_offsets, &c->niels, &c->ok, &c->msm_err, &c->results, &c->outs, &c->flags, &c->ix_pidx, &c->rp_niels, &c->rp_results, &c->rp_chal, &c->rp_raw, &c->rp_tabs, &c->pow2_tab, &c->rp_proofs, &c->rp_commit, &c->rp_par, &c->rp_contrib, &c->rp_part, &c->rp_scalars,
                       &c->rp_status, &c->rp_decbad, &c->rp_pidx, &c->rp_offsets, &c->rp_verdict, &c->rp_batch_ok, &c->rp_combined, &c->fb_scalars, &c->fb_pidx, &c->fb_offsets};
     for (DevBuf *b : bufs) b->release();
     for (MsmArena *ar : {&c->ar_gen, &c->ar_rp}) for (DevBuf *b : {&ar->counts, &ar->starts, &ar->cursor, &ar->order, &ar->sorted, &ar->buckets, &ar->wsums}) b->release();
@@ -286,6 +288,7 @@ void bp_ctx_destroy(bp_ctx *c) {
 }
 const char *bp_last_error(const bp_ctx *c) { return c ? c->err.c_str() : "null context"; }
 uint64_t bp_ctx_launch_count(const bp_ctx *c) { return c ? c->launches : 0; }
+int bp_ctx_set_msm_window(bp_ctx *c, int window_bits) { if (!c || window_bits < 0 || window_bits > 18 || window_bits == 1) return BP_ERR_INVALID_ARGUMENT; c->msm_window = window_bits; return BP_OK; }
 int bp_ctx_synchronize(bp_ctx *c) { if (!c) return BP_ERR_INVALID_ARGUMENT; CK(c, cudaSetDevice(c->device)); CK(c, cudaStreamSynchronize(c->stream)); return BP_OK; }
 
 int bp_decompress_check_batch(bp_ctx *c, const uint8_t *points, size_t n, uint8_t *ok) {
@@ -564,7 +567,7 @@ static int rp_ensure(bp_ctx *c, const rp_geom &g) {
     CK(c, c->rp_pidx.ensure(TT * 4)); CK(c, c->rp_offsets.ensure(((size_t)g.nbatch + 1) * 4)); CK(c, c->rp_results.ensure((size_t)g.nbatch * sizeof(ge_ext)));
     CK(c, c->rp_batch_ok.ensure((size_t)g.nbatch * 4)); CK(c, c->rp_combined.ensure((size_t)g.nbatch * 4));
     CK(c, c->rp_chal.ensure(total * sizeof(rp_head))); CK(c, c->rp_tabs.ensure(total * rp_tab_size(g.k, g.m) * sizeof(sc)));
-    CK(c, c->rp_raw.ensure(total * (RP_RAW_U + g.k) * 64)); CK(c, c->rp_work.ensure(total * sizeof(rp_work)));
+    CK(c, c->rp_raw.ensure(total * (RP_RAW_U + g.k) * 64));
     if (!c->h_verdict || c->h_verdict_cap < total) {
         if (c->h_verdict) cudaFreeHost(c->h_verdict);
         c->h_verdict = nullptr; c->h_verdict_cap = 0;
@@ -582,7 +585,7 @@ static int rp_ensure(bp_ctx *c, const rp_geom &g) {
 // signature of every device address the launch sequence of a group bakes into its graph: a regrown (moved) arena invalidates the graph
 static uint64_t rp_ptr_signature(const bp_ctx *c) {
     const DevBuf *bufs[] = {&c->rp_par, &c->rp_contrib, &c->rp_part, &c->rp_scalars, &c->rp_status, &c->rp_decbad, &c->rp_niels, &c->rp_pidx, &c->rp_offsets, &c->rp_results, &c->rp_batch_ok, &c->rp_combined,
-                            &c->rp_chal, &c->rp_tabs, &c->rp_raw, &c->rp_work, &c->pow2_tab, &c->ar_rp.counts, &c->ar_rp.starts, &c->ar_rp.cursor, &c->ar_rp.order, &c->ar_rp.sorted, &c->ar_rp.buckets, &c->ar_rp.wsums};
+                            &c->rp_chal, &c->rp_tabs, &c->rp_raw, &c->pow2_tab, &c->ar_rp.counts, &c->ar_rp.starts, &c->ar_rp.cursor, &c->ar_rp.order, &c->ar_rp.sorted, &c->ar_rp.buckets, &c->ar_rp.wsums};
     uint64_t h = 1469598103934665603ULL;
     for (const DevBuf *b : bufs) { h ^= (uint64_t)(uintptr_t)b->p; h *= 1099511628211ULL; }
     return h;
@@ -633,8 +636,7 @@ static int rp_chain(bp_ctx *c, bp_gens *gens, const rp_geom &g) {
         if (rc) return rc;
     }
     if (s2 != s) CK(c, cudaEventRecord(c->ev_join, s2));
-    const size_t tr_smem = RP_TR_ROWS_BYTES + (size_t)RP_TR_THREADS * (g.proof_len + 32 * g.m);
-    LAUNCH(c, KID_RP_TRANSCRIPT, k_rp_transcript<<<blocks_for(total, RP_TR_THREADS), RP_TR_THREADS, tr_smem, s>>>(par, g, total, c->rp_raw.as<uint8_t>(), c->rp_status.as<uint32_t>()));
+    LAUNCH(c, KID_RP_TRANSCRIPT, k_rp_transcript<<<blocks_for(total, RP_TR_THREADS), RP_TR_THREADS, 0, s>>>(par, g, total, c->rp_raw.as<uint8_t>(), c->rp_status.as<uint32_t>()));
     LAUNCH(c, KID_RP_HEAD, k_rp_head_seq<<<blocks_for(total, 32), 32, 0, s>>>(par, g, c->rp_raw.as<uint8_t>(), total, c->rp_chal.as<rp_head>(), c->rp_tabs.as<sc>(),
                                                                                   c->pow2_tab.as<sc>(), c->rp_status.as<uint32_t>()));
     if (s2 != s) CK(c, cudaStreamWaitEvent(s, c->ev_join, 0));

@@ -228,48 +228,7 @@ BP_HD void fe_mul_wide(uint32_t t[16], const fe &A, const fe &B) {
 // r = (t[0..7] + 38 * t[8..15]) folded below 2^256
 BP_HD fe fe_reduce_wide(const uint32_t t[16]) {
     fe r;
-#if defined(__CUDA_ARCH__) && defined(BP_FOLD_ALU)
-    // 38 h = (h << 5) + (h << 2) + (h << 1): funnel shifts and three carry chains on the ALU pipe instead of eight wide multiplies on the
-    // integer-multiply pipe, which is the pipe that binds every field-arithmetic kernel (fe_mul: 72 -> 64 IMAD.WIDE, fe_sq: 44 -> 36)
-    uint32_t r0, r1, r2, r3, r4, r5, r6, r7, r8;
-    {
-        const uint32_t h0 = t[8], h1 = t[9], h2 = t[10], h3 = t[11], h4 = t[12], h5 = t[13], h6 = t[14], h7 = t[15];
-        uint32_t a0 = h0 << 5, a1 = __funnelshift_l(h0, h1, 5), a2 = __funnelshift_l(h1, h2, 5), a3 = __funnelshift_l(h2, h3, 5), a4 = __funnelshift_l(h3, h4, 5),
-                 a5 = __funnelshift_l(h4, h5, 5), a6 = __funnelshift_l(h5, h6, 5), a7 = __funnelshift_l(h6, h7, 5), a8 = h7 >> 27;
-        asm("add.cc.u32 %0, %9, %18;\n\t addc.cc.u32 %1, %10, %19;\n\t addc.cc.u32 %2, %11, %20;\n\t addc.cc.u32 %3, %12, %21;\n\t"
-            "addc.cc.u32 %4, %13, %22;\n\t addc.cc.u32 %5, %14, %23;\n\t addc.cc.u32 %6, %15, %24;\n\t addc.cc.u32 %7, %16, %25;\n\t addc.u32 %8, %17, 0;\n\t"
-            : "=&r"(r0), "=&r"(r1), "=&r"(r2), "=&r"(r3), "=&r"(r4), "=&r"(r5), "=&r"(r6), "=&r"(r7), "=&r"(r8)
-            : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(a4), "r"(a5), "r"(a6), "r"(a7), "r"(a8),
-              "r"(t[0]), "r"(t[1]), "r"(t[2]), "r"(t[3]), "r"(t[4]), "r"(t[5]), "r"(t[6]), "r"(t[7]));
-        uint32_t b0 = h0 << 2, b1 = __funnelshift_l(h0, h1, 2), b2 = __funnelshift_l(h1, h2, 2), b3 = __funnelshift_l(h2, h3, 2), b4 = __funnelshift_l(h3, h4, 2),
-                 b5 = __funnelshift_l(h4, h5, 2), b6 = __funnelshift_l(h5, h6, 2), b7 = __funnelshift_l(h6, h7, 2), b8 = h7 >> 30;
-        asm("add.cc.u32 %0, %0, %9;\n\t addc.cc.u32 %1, %1, %10;\n\t addc.cc.u32 %2, %2, %11;\n\t addc.cc.u32 %3, %3, %12;\n\t"
-            "addc.cc.u32 %4, %4, %13;\n\t addc.cc.u32 %5, %5, %14;\n\t addc.cc.u32 %6, %6, %15;\n\t addc.cc.u32 %7, %7, %16;\n\t addc.u32 %8, %8, %17;\n\t"
-            : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(r8)
-            : "r"(b0), "r"(b1), "r"(b2), "r"(b3), "r"(b4), "r"(b5), "r"(b6), "r"(b7), "r"(b8));
-        uint32_t c0 = h0 << 1, c1 = __funnelshift_l(h0, h1, 1), c2 = __funnelshift_l(h1, h2, 1), c3 = __funnelshift_l(h2, h3, 1), c4 = __funnelshift_l(h3, h4, 1),
-                 c5 = __funnelshift_l(h4, h5, 1), c6 = __funnelshift_l(h5, h6, 1), c7 = __funnelshift_l(h6, h7, 1), c8_ = h7 >> 31;
-        asm("add.cc.u32 %0, %0, %9;\n\t addc.cc.u32 %1, %1, %10;\n\t addc.cc.u32 %2, %2, %11;\n\t addc.cc.u32 %3, %3, %12;\n\t"
-            "addc.cc.u32 %4, %4, %13;\n\t addc.cc.u32 %5, %5, %14;\n\t addc.cc.u32 %6, %6, %15;\n\t addc.cc.u32 %7, %7, %16;\n\t addc.u32 %8, %8, %17;\n\t"
-            : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "+r"(r8)
-            : "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4), "r"(c5), "r"(c6), "r"(c7), "r"(c8_));
-    }
-    // r8 <= 39: fold once more, then a last conditional +38
-    uint32_t k = (r8 << 5) + (r8 << 2) + (r8 << 1), c2_;
-    asm("add.cc.u32 %0, %0, %9;\n\t"
-        "addc.cc.u32 %1, %1, 0;\n\t"
-        "addc.cc.u32 %2, %2, 0;\n\t"
-        "addc.cc.u32 %3, %3, 0;\n\t"
-        "addc.cc.u32 %4, %4, 0;\n\t"
-        "addc.cc.u32 %5, %5, 0;\n\t"
-        "addc.cc.u32 %6, %6, 0;\n\t"
-        "addc.cc.u32 %7, %7, 0;\n\t"
-        "addc.u32 %8, 0, 0;\n\t"
-        : "+r"(r0), "+r"(r1), "+r"(r2), "+r"(r3), "+r"(r4), "+r"(r5), "+r"(r6), "+r"(r7), "=&r"(c2_)
-        : "r"(k));
-    r0 += (c2_ << 5) + (c2_ << 2) + (c2_ << 1);
-    r.v[0] = r0; r.v[1] = r1; r.v[2] = r2; r.v[3] = r3; r.v[4] = r4; r.v[5] = r5; r.v[6] = r6; r.v[7] = r7;
-#elif defined(__CUDA_ARCH__)
+#ifdef __CUDA_ARCH__
     uint32_t r0 = t[0], r1 = t[1], r2 = t[2], r3 = t[3], r4 = t[4], r5 = t[5], r6 = t[6], r7 = t[7], ce;
     uint32_t u0, u1, u2, u3, u4, u5, u6, u7;
     const uint32_t k38 = 38u;

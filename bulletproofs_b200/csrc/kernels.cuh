@@ -138,11 +138,6 @@ __global__ void __launch_bounds__(128) k_compress(const ge_ext *__restrict__ in,
     if (i >= n) return;
     uint8_t s[32]; ge_encode(s, ld_ext(in + i)); st32(out + 32 * i, s);
 }
-__global__ void k_is_identity(const ge_ext *__restrict__ in, size_t n, uint32_t *__restrict__ flags) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    flags[i] = ge_is_identity(ld_ext(in + i)) ? 1u : 0u;
-}
 
 // ------------------------------------------------------------------ K7: from_uniform_bytes (generator chain)
 // in: n x 64 B.  out: affine-Niels table entry and/or compressed bytes.
@@ -287,7 +282,7 @@ __global__ void __launch_bounds__(256) k_msm_scatter(const uint8_t *__restrict__
     }
 }
 // heavy buckets (size >= heavy_min, listed by k_msm_order): one 128-thread block per bucket, grid-stride over the list: threads take
-// strided entries, then a shuffle tree + one shared-memory round add the partial sums.  Runs in the tail blocks of k_msm_accumulate's
+// strided entries, then a shuffle tree + one shared-memory round add the partial sums.  Runs in the first blocks of k_msm_accumulate's
 // grid (a separate launch would wait for an SM with a free block slot behind the wide kernels of the other groups in flight).
 #define MSM_ACC_THREADS 128
 __device__ __noinline__ void msm_heavy_role(const uint32_t *__restrict__ starts, const uint32_t *__restrict__ ends, const uint32_t *__restrict__ sorted,
@@ -332,11 +327,12 @@ __global__ void __launch_bounds__(128, 5) k_msm_accumulate(const uint32_t *__res
                                                         const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ order, int W, uint32_t nb, size_t n_buckets,
                                                         const uint32_t *__restrict__ point_idx, const ge_niels *__restrict__ pts_static, const ge_niels *__restrict__ pts_dynamic,
                                                         ge_ext *__restrict__ buckets, uint32_t heavy_min, uint32_t n_light_blocks, const uint32_t *__restrict__ heavy_n, const uint32_t *__restrict__ heavy) {
-    if (blockIdx.x >= n_light_blocks) {       // the grid's tail blocks own the heavy buckets (listed by k_msm_order), one block per bucket
-        msm_heavy_role(starts, ends, sorted, offsets, heavy_n, heavy, W, nb, point_idx, pts_static, pts_dynamic, buckets, blockIdx.x - n_light_blocks, gridDim.x - n_light_blocks);
+    const uint32_t n_heavy_blocks = gridDim.x - n_light_blocks;
+    if (blockIdx.x < n_heavy_blocks) {        // the grid's FIRST blocks own the heavy buckets (listed by k_msm_order), one block per bucket: the longest work starts first
+        msm_heavy_role(starts, ends, sorted, offsets, heavy_n, heavy, W, nb, point_idx, pts_static, pts_dynamic, buckets, blockIdx.x, n_heavy_blocks);
         return;
     }
-    size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t tid = (size_t)(blockIdx.x - n_heavy_blocks) * blockDim.x + threadIdx.x;
     size_t b = tid / SPLIT; uint32_t sub = (uint32_t)(tid % SPLIT);
     bool live = b < n_buckets;
     if (SPLIT == 1 && !live) return;
@@ -593,116 +589,24 @@ __device__ __forceinline__ uint32_t rp_eff_status(uint32_t st, uint32_t dec_bad)
     return st != BP_PROOF_OK ? st : (dec_bad ? (uint32_t)BP_PROOF_VERIFICATION_ERROR : (uint32_t)BP_PROOF_OK);
 }
 
-// K6: transcript replay (pure hashing).  One thread per proof (32 proofs per warp, identical control flow, every lane busy).  The block's
-// 32 proofs and their commitments are staged into shared memory by the TMA engine (two bulk copies, tma_stage_two): the replay reads
-// every proof byte once, one byte at a time at arbitrary offsets, which from shared memory costs an LDS instead of an L2 round trip.
-// The STROBE state of each thread is a padded shared-memory row (stride 204 B: conflict-free byte access).
+// K6: transcript replay (pure hashing).  One thread per proof (32 proofs per warp, identical control flow, every lane busy); the STROBE
+// state of each thread is a padded shared-memory row (stride 204 B: conflict-free byte access).  The proof bytes are read straight from
+// global memory: staging the block's 32 proofs (21 KB) in shared memory through the TMA engine was built and measured -- same solo
+// duration (the kernel is bound by its ~22 Keccak-f per proof, not by the byte loads) and 4 % less throughput for the whole mix, because
+// 29 KB of shared memory per 32-thread block changes what can be co-resident on an SM (profiles/r2_experiments.md).
 #define RP_TR_THREADS 32
-#define RP_TR_ROWS_BYTES 6656           // 32 x 204 rounded up to a multiple of 128
 __global__ void __launch_bounds__(RP_TR_THREADS) k_rp_transcript(const rp_params *__restrict__ par, rp_geom g, uint32_t total,
                                                                    uint8_t *__restrict__ raw, uint32_t *__restrict__ status) {
-    extern __shared__ __align__(128) uint8_t tr_smem[];
-    __shared__ __align__(8) uint64_t bar;
-    uint8_t (*rows)[204] = reinterpret_cast<uint8_t (*)[204]>(tr_smem);
-    uint8_t *sp = tr_smem + RP_TR_ROWS_BYTES, *sv = sp + RP_TR_THREADS * g.proof_len;
-    const uint32_t p0 = blockIdx.x * blockDim.x, cnt = min((uint32_t)blockDim.x, total - p0), p = p0 + threadIdx.x;
-    tma_stage_two(sp, par->proofs + (size_t)p0 * g.proof_len, cnt * g.proof_len, sv, par->commitments + (size_t)p0 * g.m * 32, cnt * g.m * 32, &bar);
+    __shared__ __align__(16) uint8_t rows[RP_TR_THREADS][204];
+    uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= total) return;
+    const uint8_t *proof = par->proofs + (size_t)p * g.proof_len, *V = par->commitments + (size_t)p * g.m * 32;
     uint8_t (*my)[64] = reinterpret_cast<uint8_t (*)[64]>(raw + (size_t)p * (RP_RAW_U + g.k) * 64);
-    status[p] = rp_transcript_raw(my, sp + threadIdx.x * g.proof_len, g.k, sv + threadIdx.x * g.m * 32, g.n, g.m, par->tstate, par->seed, rows[threadIdx.x]);
-}
-// Cooperative head: the ~180 Montgomery products of one proof's shared scalars and tables (rp_scalars_head is the sequential
-// statement of the same values) are split over RP_HEAD_WARPS warps; lane = proof, so every warp runs one straight-line task
-// for 32 proofs and the block synchronises between the four dependency phases.  Writes heads[p] and the proof's tables.
-#define RP_HEAD_WARPS 8
-__global__ void __launch_bounds__(32 * RP_HEAD_WARPS) k_rp_head(const rp_params *__restrict__ par, rp_geom g, const uint8_t *__restrict__ raw, uint32_t count,
-                                                               rp_head *__restrict__ heads, sc *__restrict__ tabs, const sc *__restrict__ pow2,
-                                                               rp_work *__restrict__ work, uint32_t *__restrict__ status) {
-    const uint8_t *proofs = par->proofs;
-    const uint32_t lane = threadIdx.x & 31, wq = threadIdx.x >> 5, p = blockIdx.x * 32 + lane;
-    const bool in = p < count;
-    const uint32_t pc = in ? p : count - 1;
-    const uint32_t k = g.k, n = g.n, m = g.m, kl = rp_kl(k), kh = k - kl, TL = 1u << kl, TH = 1u << kh;
-    bool ok = in && status[pc] == BP_PROOF_OK;
-    const uint8_t *proof = proofs + (size_t)pc * g.proof_len, *rw = raw + (size_t)pc * (RP_RAW_U + k) * 64;
-    rp_work &W = work[pc]; rp_head &h = heads[pc];
-    rp_tabs T = rp_tab_ptrs(tabs + (size_t)pc * rp_tab_size(k, m), k);
-    // ---- phase A: reduce the challenges mod l, proof scalars to Montgomery form
-    if (ok) for (uint32_t it = wq; it < RP_RAW_U + k + 5; it += RP_HEAD_WARPS) {
-        if (it < RP_RAW_U + k) { sc v = rp_wide(rw + 64 * it); if (it < RP_RAW_U) W.ch[it] = v; else W.u[it - RP_RAW_U] = v; }
-        else {
-            uint32_t j = it - RP_RAW_U - k;                 // a, b, t_x, t_x_blinding, e_blinding
-            const uint8_t *src = j < 2 ? proof + 224 + 64 * k + 32 * j : proof + 128 + 32 * (j - 2);
-            W.pf[j] = sc_to_mont(sc_load(src));
-        }
-    }
-    __syncthreads();
-    if (ok) {       // zero challenges: see rp_transcript; every warp takes the same decision
-        bool bad = sc_is_zero(W.ch[RP_RAW_Y]);
-        for (uint32_t j = 0; j < k; j++) bad = bad || sc_is_zero(W.u[j]);
-        if (bad) { ok = false; if (wq == 0) status[p] = BP_PROOF_VERIFICATION_ERROR; }
-    }
-    if (wq == 0 && in) h.status = ok ? (uint32_t)BP_PROOF_OK : (status[p] == BP_PROOF_OK ? (uint32_t)BP_PROOF_VERIFICATION_ERROR : status[p]);
-    sc y, z, rho;
-    if (ok) { y = W.ch[RP_RAW_Y]; z = W.ch[RP_RAW_Z]; rho = W.ch[RP_RAW_RHO]; if (sc_is_zero(rho)) rho = sc_mont_one(); }
-    // ---- phase B: the serial chains, one per warp
-    if (ok) switch (wq) {
-    case 0: { sc pre = sc_mont_one(); h.pre[0] = pre; for (uint32_t j = 0; j < k; j++) { sc us = sc_mm(W.u[j], W.u[j]); h.u_sq[j] = us; pre = sc_mm(pre, us); h.pre[j + 1] = pre; } } break;
-    case 1: { sc suf = sc_mont_one(); h.suf[k] = suf; for (int j = (int)k - 1; j >= 0; j--) { suf = sc_mm(suf, sc_mm(W.u[j], W.u[j])); h.suf[j] = suf; } } break;
-    case 2: { sc U = sc_mont_one(); for (uint32_t j = 0; j < k; j++) U = sc_mm(U, W.u[j]);
-              sc rhoU = sc_mm(rho, U); W.U = U; W.rhoU = rhoU; h.hB = sc_mm(W.pf[1], rhoU); W.hA = sc_mm(sc_mm(rhoU, U), sc_mm(z, z)); } break;
-    case 3: { sc yp = y, Y = y; W.ypow2[0] = yp; for (uint32_t j = 1; j < k; j++) { yp = sc_mm(yp, yp); W.ypow2[j] = yp; Y = sc_mm(Y, yp); }
-              if (k == 0) Y = sc_mont_one();
-              W.Y = Y; h.rhoY = sc_mm(rho, Y); } break;
-    case 4: { sc sum_y = rp_sum_of_powers_pow2(y, (uint64_t)n * m); W.t1 = sc_mm(sc_sub(z, sc_mm(z, z)), sum_y); } break;
-    case 5: { sc zz = sc_mm(z, z); h.z = z; h.zz = zz;
-              sc sum_z = rp_sum_of_powers_pow2(z, m), sum_2 = sc_mont_from_u64(n == 64 ? ~0ULL : ((1ULL << n) - 1));
-              W.d2 = sc_mm(sc_mm(sc_mm(zz, z), sum_2), sum_z); } break;
-    case 6: { const sc &a = W.pf[0], &b = W.pf[1], &t_x = W.pf[2], &w = W.ch[RP_RAW_W], &c = W.ch[RP_RAW_C];
-              W.e1 = sc_sub(sc_mm(w, sc_sub(t_x, sc_mm(a, b))), sc_mm(c, t_x));
-              W.bl = sc_neg(sc_add(W.pf[4], sc_mm(c, W.pf[3]))); } break;
-    default: break;
-    }
-    __syncthreads();
-    // ---- phase C: the four subset-product tables, the lambda chain, gA
-    if (ok) switch (wq) {
-    case 0: RP_BUILD_TABLE(T.s_lo, kl, h.u_sq[(k - 1) - b_]); break;
-    case 1: RP_BUILD_TABLE(T.s_hi, kh, h.u_sq[(k - 1) - kl - b_]); break;
-    case 2: RP_BUILD_TABLE(T.y_lo, kl, W.ypow2[b_]); break;
-    case 3: RP_BUILD_TABLE(T.y_hi, kh, W.ypow2[kl + b_]); break;
-    case 4: { const sc &x = W.ch[RP_RAW_X], &c = W.ch[RP_RAW_C];
-              sc L = sc_mm(rho, sc_mm(h.pre[k], W.Y)); h.L = L; h.zL = sc_mm(z, L);
-              sc Lx = sc_mm(L, x), Lcx = sc_mm(Lx, c); h.Lx = Lx; h.Lcx = Lcx; h.Lcxx = sc_mm(Lcx, x); h.Lczz = sc_mm(sc_mm(L, c), sc_mm(z, z));
-              // basepoint scalar w (t_x - a b) + c (delta - t_x) = e1 + c delta,  delta = t1 - d2   (mod.rs:419, 587-593);  blinding scalar -e~ - c t~  (mod.rs:430)
-              sc bs = sc_add(W.e1, sc_mm(c, sc_sub(W.t1, W.d2)));
-              h.basepoint_scalar = sc_mm(L, bs); h.blinding_scalar = sc_mm(L, W.bl); } break;
-    case 5: h.gA = sc_mm(sc_mm(W.pf[0], W.rhoU), W.Y); break;
-    default: break;
-    }
-    __syncthreads();
-    // ---- phase D: the mixed tables, entries dealt round-robin to four warps each
-    if (ok) {
-        if (wq < 4) {
-            for (uint32_t v = wq; v < TL; v += 4) {
-                sc F = sc_mm(pow2[v % n], rp_pow_small(z, v / n));
-                T.P_lo[v] = sc_mm(T.y_lo[v ^ (TL - 1)], F);
-                T.Q_lo[v] = sc_mm(T.y_lo[v ^ (TL - 1)], T.s_lo[v ^ (TL - 1)]);
-            }
-        } else {
-            for (uint32_t v = wq - 4; v < TH; v += 4) {
-                uint64_t idx = (uint64_t)v << kl;
-                sc F = sc_mm(pow2[idx % n], rp_pow_small(z, (uint32_t)(idx / n)));
-                sc yc = T.y_hi[v ^ (TH - 1)];
-                T.A_hi[v] = sc_mm(h.gA, T.s_hi[v]);
-                T.P_hi[v] = sc_mm(sc_mm(W.hA, yc), F);
-                T.Q_hi[v] = sc_mm(sc_mm(h.hB, yc), T.s_hi[v ^ (TH - 1)]);
-            }
-        }
-    }
+    status[p] = rp_transcript_raw(my, proof, g.k, V, g.n, g.m, par->tstate, par->seed, rows[threadIdx.x]);
 }
 // Lean head: ONE thread per proof runs the sequential statement (rp_scalars_head) -- ~180 dependent Montgomery products.  Several
 // groups are in flight, so a head's latency is hidden; what counts is its footprint: one warp per 32 proofs here against eight
-// (a 256-thread block at 100 registers per 32 proofs = two thirds of the GPU's register file for a whole group) in k_rp_head.
+// (a 256-thread block at 100 registers per 32 proofs = two thirds of the GPU's register file for a whole group) in the round-1 cooperative head.
 __global__ void __launch_bounds__(32) k_rp_head_seq(const rp_params *__restrict__ par, rp_geom g, const uint8_t *__restrict__ raw, uint32_t total,
                                                     rp_head *__restrict__ heads, sc *__restrict__ tabs, const sc *__restrict__ pow2, uint32_t *__restrict__ status) {
     uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -723,7 +627,7 @@ __global__ void __launch_bounds__(32) k_rp_head_seq(const rp_params *__restrict_
 }
 // K5 (combined check): verification scalars with the sum over the proofs taken in registers.  Block = (chunk of RP_CHUNK proofs of one
 // batch); thread = generator index i: it walks the chunk's proofs and adds up their weighted g_i and h_i (three Montgomery products
-// per proof and index), so the count x S per-proof array of the per-proof form below is never written; k_rp_static_reduce then adds
+// per proof and index), so the count x S per-proof array of the per-proof form below is never written; k_rp_static_sum then adds
 // the few per-chunk partial sums.  The same block also writes the chunk's per-proof ("dynamic") scalars into the MSM scalar array.
 #define RP_CHUNK 32
 __global__ void __launch_bounds__(128) k_rp_scalars_sum(rp_geom g, const rp_head *__restrict__ heads, const sc *__restrict__ tabs, const uint32_t *__restrict__ dec_bad,
@@ -825,24 +729,6 @@ __global__ void __launch_bounds__(RP_DEC_THREADS, 5) k_rp_decompress(const rp_pa
     fe x, y; bool valid = ge_decode(x, y, s);
     st_niels(out + i, valid ? ge_to_niels_affine(x, y) : ge_niels_identity());
     if (!valid) dec_bad[p] = 1u;
-}
-// sum the weighted static-term scalars over the proofs of a batch: one block per (static term, batch)
-__global__ void __launch_bounds__(128) k_rp_static_reduce(const sc *__restrict__ contrib, rp_geom g, uint8_t *__restrict__ scal) {
-    __shared__ sc sm[4];
-    uint32_t s = blockIdx.x, b = blockIdx.y;
-    const sc *mine = contrib + (size_t)b * g.count * g.S;
-    sc acc = sc_zero();
-    for (uint32_t p = threadIdx.x; p < g.count; p += blockDim.x) acc = sc_add(acc, mine[(size_t)p * g.S + s]);
-    for (int d = 16; d >= 1; d >>= 1) {
-        sc o; for (int i = 0; i < 8; i++) o.v[i] = __shfl_down_sync(0xffffffffu, acc.v[i], d);
-        acc = sc_add(acc, o);
-    }
-    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (uint32_t k = 1; k < (blockDim.x >> 5); k++) acc = sc_add(acc, sm[k]);
-        uint8_t bytes[32]; sc_store(bytes, sc_from_mont(acc)); st32(scal + ((size_t)b * g.T + s) * 32, bytes);
-    }
 }
 // fallback, first level: one combined MSM per chunk of RP_CHUNK proofs of a failing batch.  Everything is already there: the chunk's
 // summed static-term scalars (k_rp_scalars_sum's partial sums) and its proofs' dynamic scalars.  Rows are [S static | RP_CHUNK*D dynamic],

@@ -24,19 +24,17 @@ BP_HD int msm_digit(const msm_wide &r, int w, int c) {
     uint32_t raw = (uint32_t)(two >> sh) & ((1u << c) - 1u);
     return (int)raw - (1 << (c - 1));
 }
-// window size by terms per MSM (tuned on B200)
+// window size by terms per MSM (tuned on B200).  Scalars are < l ~ 2^252, so a window size c that divides 252 leaves the
+// top window nothing but the recoding carry: HALF of all terms land in its bucket 0 (one thread -- or one heavy-bucket block -- adds
+// n/2 points while the other buckets hold n/2^(c-1)).  From 17 terms up the table therefore only uses c in {5, 8, 10, 11, 13, 15, 16}.
 BP_HD int msm_pick_window(size_t avg_terms) {
     if (avg_terms <= 8) return 3;
-    if (avg_terms <= 32) return 4;
-    if (avg_terms <= 96) return 5;
-    if (avg_terms <= 256) return 6;
-    if (avg_terms <= 768) return 7;
-    if (avg_terms <= 2048) return 8;
-    if (avg_terms <= 6144) return 9;
-    if (avg_terms <= 16384) return 10;
+    if (avg_terms <= 16) return 4;
+    if (avg_terms <= 384) return 5;
+    if (avg_terms <= 2560) return 8;
+    if (avg_terms <= 8192) return 10;
     if (avg_terms <= 49152) return 11;
-    if (avg_terms <= 131072) return 12;
-    if (avg_terms <= 393216) return 13;
-    if (avg_terms <= 1048576) return 14;
-    return 15;
+    if (avg_terms <= 262144) return 13;
+    if (avg_terms <= 1572864) return 15;
+    return 16;
 }

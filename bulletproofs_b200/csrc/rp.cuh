@@ -117,14 +117,6 @@ struct rp_head {                // Montgomery form; "L" = Lambda = rho * lambda
     sc basepoint_scalar, blinding_scalar;
 };
 
-// Scratch of the cooperative head kernel (k_rp_head), one per proof, Montgomery form
-struct rp_work {
-    sc ch[6];                       // y, z, x, w, c, rho  (RP_RAW_* order)
-    sc pf[5];                       // a, b, t_x, t_x_blinding, e_blinding
-    sc u[BP_MAX_LG_N], ypow2[BP_MAX_LG_N];
-    sc U, Y, rhoU, hA, t1, d2, e1, bl;
-};
-
 // Per-proof product tables (global memory, rp_tab_size() scalars per proof) that turn the tail into three products
 // per generator index.  The k index bits are split in a low group of kl = ceil(k/2) bits (TL = 2^kl values) and a
 // high group of kh = k - kl bits (TH = 2^kh values), i = hi*TL + lo, and ~v is the complement within the group:

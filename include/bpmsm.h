@@ -56,6 +56,9 @@ void bp_ctx_destroy(bp_ctx *ctx);
 const char *bp_last_error(const bp_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t bp_ctx_launch_count(const bp_ctx *ctx);
+/* Pippenger window size (bits) of the generic MSM entry points on this context: 0 = chosen by terms per MSM (default), 2..18 = fixed.
+ * Results do not depend on it; tests use it to cover every window geometry, benchmarks to tune. */
+int bp_ctx_set_msm_window(bp_ctx *ctx, int window_bits);
 /* block until all work queued on the context's stream is finished */
 int bp_ctx_synchronize(bp_ctx *ctx);
 

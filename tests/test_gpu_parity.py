@@ -403,3 +403,20 @@ def test_resident_point_set_msm(gpu_ctx, orc, terms, n_msm):
     ps.close()
     with pytest.raises(bp.BpError):
         bp.PointSet(gpu_ctx, pts[:64] + b"\x01" + bytes(31))
+
+
+@pytest.mark.parametrize("window", [2, 3, 5, 8, 9, 12, 13, 16])
+def test_msm_every_window_geometry(gpu_ctx, orc, window):
+    """The result of an MSM does not depend on the Pippenger window: pin it (bp_ctx_set_msm_window) and compare with the oracle, including the
+    windows with c*(W-1) = 252 whose top window holds only the recoding carry (c = 9, 12) and windows wider than the MSM is long."""
+    rnd = random.Random(300 + window)
+    base = [orc.from_uniform(rnd.randbytes(64)) for _ in range(40)]
+    try:
+        gpu_ctx.set_msm_window(window)
+        for n in (1, 37, 700):
+            sc = b"".join(le(rnd.randrange(l)) for _ in range(n)); pp = b"".join(rnd.choice(base) for _ in range(n))
+            assert gpu_ctx.msm(sc, pp) == orc.msm(sc, pp), (window, n)
+        sc = b"".join(le(x) for x in (0, 1, l - 1, 2**252, 2**128, l - 2**200, 2**252 + 1, 5)); pp = b"".join(base[:8])
+        assert gpu_ctx.msm(sc, pp) == orc.msm(sc, pp)
+    finally:
+        gpu_ctx.set_msm_window(0)

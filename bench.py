@@ -372,9 +372,17 @@ def main():
     proofs_per_step = S * G * BATCH
 
     # ---- value: inputs resident in HBM
+    # at most two groups queued per stream (the host-buffer path below has one): a deeper queue only adds driver back-pressure on the issuing threads
+    dev_ev = [[torch.cuda.Event(), torch.cuda.Event()] for _ in range(S)]
+    dev_cnt = [0] * S
+
     def group_dev(i, k):
         j = (i * S + k) % P
+        e = dev_ev[k][dev_cnt[k] & 1]
+        if dev_cnt[k] >= 2:
+            e.synchronize()
         ver[k].run_device(d_proofs[j].data_ptr(), d_vs[j].data_ptr(), d_verdicts[k].data_ptr(), h_ok[k].data_ptr())
+        e.record(streams[k]); dev_cnt[k] += 1
 
     clk = None
     if rank == 0:

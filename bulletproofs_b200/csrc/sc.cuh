@@ -69,6 +69,23 @@ BP_HD sc sc_mont_mul(const sc &a, const sc &b) {
     sc r;
     for (int i = 0; i < 8; i++) { c += (uint64_t)t[8 + i] + u[8 + i]; r.v[i] = (uint32_t)c; c >>= 32; }
     return sc_cond_sub_l(r);                      // sum < 2l < 2^254: c is zero here
+#elif defined(__SIZEOF_INT128__)
+    // host (the C++ mirror's scalar arithmetic, the host-emulation tests): CIOS on four 64-bit limbs with 128-bit products
+    typedef unsigned __int128 u128_;
+    const uint64_t L64[4] = {0x5812631a5cf5d3edULL, 0x14def9dea2f79cd6ULL, 0, 0x1000000000000000ULL}, LF = 0xd2b51da312547e1bULL;     // l, -l^-1 mod 2^64
+    uint64_t x[4], y[4], t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) { x[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32); y[i] = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32); }
+    for (int i = 0; i < 4; i++) {
+        u128_ c = 0;
+        for (int j = 0; j < 4; j++) { c += (u128_)x[j] * y[i] + t[j]; t[j] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[4] = (uint64_t)c; t[5] = (uint64_t)(c >> 64);
+        uint64_t m = t[0] * LF;
+        c = (u128_)m * L64[0] + t[0]; c >>= 64;
+        for (int j = 1; j < 4; j++) { c += (u128_)m * L64[j] + t[j]; t[j - 1] = (uint64_t)c; c >>= 64; }
+        c += t[4]; t[3] = (uint64_t)c; t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    sc r; for (int i = 0; i < 4; i++) { r.v[2 * i] = (uint32_t)t[i]; r.v[2 * i + 1] = (uint32_t)(t[i] >> 32); }
+    return sc_cond_sub_l(r);                      // t < 2l
 #else
     const sc l = sc_l();
     uint32_t t[10];

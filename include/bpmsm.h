@@ -95,9 +95,11 @@ int bp_msm_indexed_batch(bp_ctx *ctx, bp_gens *gens, const uint8_t *scalars, con
                          const uint8_t *dyn_points, size_t n_dyn, const uint64_t *offsets, size_t n_msm,
                          uint8_t *outs, uint8_t *status);
 
-/* ---- inner-product argument, prover side (InnerProductProof::create, inner_product_proof.rs:38-193) ---- */
-/* The generator vectors G, H (and Q) live on the device for the k rounds; the host keeps the transcript and
- * the scalar vectors a, b and calls once per round for L,R and once for the fold. */
+/* ---- inner-product argument, prover side, folding form ---------------------------------------- */
+/* The generator vectors G, H (and Q) live on the device for the k rounds and are folded there; the host keeps the transcript and
+ * the scalar vectors a, b and calls once per round for L,R and once for the fold.  This is the form LinearProof::create
+ * (linear_proof.rs:40-160) runs on; InnerProductProof::create (inner_product_proof.rs:38-193) uses the bp_ippx_* session below,
+ * which keeps a and b on the device as well and never folds a point. */
 typedef struct bp_ipp bp_ipp;
 /* G = bp_gens.G(n, m), H = bp_gens.H(n, m) (N = n*m points each), Q compressed */
 int bp_ipp_begin(bp_ctx *ctx, bp_gens *gens, size_t n, size_t m, const uint8_t Q[32], bp_ipp **out);
@@ -209,6 +211,9 @@ int bp_rangeproof_verify_group_begin(bp_ctx *ctx, bp_gens *gens, const uint8_t t
                                      const uint8_t *proofs, size_t proof_len, const uint8_t *commitments,
                                      size_t n, size_t m, size_t count, size_t n_batches, const uint8_t seed[32]);
 int bp_rangeproof_verify_group_finish(bp_ctx *ctx, uint8_t *verdicts, uint8_t *batch_ok);
+/* Between *_begin and *_finish the context's arenas belong to the pending verification (its reject path reads them): every other
+ * entry point on that context returns BP_ERR_INVALID_ARGUMENT with a message in bp_last_error(); use another context for concurrent work.
+ * A failed *_begin leaves nothing pending. */
 /* device-resident form (see bp_rangeproof_verify_batch_device); h_batch_ok_pinned (optional, pinned): n_batches x uint32 */
 int bp_rangeproof_verify_group_device(bp_ctx *ctx, bp_gens *gens, const uint8_t transcript[BP_TRANSCRIPT_BYTES],
                                       const void *d_proofs, size_t proof_len, const void *d_commitments,

@@ -77,3 +77,25 @@ def test_config3_full_size_batch(gpu_ctx, orc):
     assert [i for i, v in enumerate(got) if v] == [3, 200]
     assert got[:16] == orc.verify_many(og, orc.transcript(label), bytes(pb[:16 * plen]), plen, bytes(vb[:16 * 32 * m]), n, m, 16)
     gens.close()
+
+
+def test_resident_point_set_large(gpu_ctx, orc):
+    """bp_points at sweep size: 2 MSMs of 2^18 terms over one resident set (points tiled from 512 bases, so the result equals a 512-term
+    oracle MSM over the folded scalars); the decompress-every-call path gives the same bytes."""
+    import bulletproofs_b200 as bp
+    n, b, K = 1 << 18, 512, 2
+    rnd = random.Random(1818)
+    base = [orc.from_uniform(rnd.randbytes(64)) for _ in range(b)]
+    pts = b"".join(base) * (n // b)
+    ps = bp.PointSet(gpu_ctx, pts)
+    scalars = [[rnd.randrange(l) for _ in range(n)] for _ in range(K)]
+    sc = b"".join(le(s) for row in scalars for s in row)
+    st, outs = ps.msm(sc, K, n)
+    assert st == [0] * K
+    for j in range(K):
+        folded = [0] * b
+        for i, s in enumerate(scalars[j]):
+            folded[i % b] += s
+        assert (0, outs[j]) == orc.msm(b"".join(le(f % l) for f in folded), b"".join(base)), j
+    assert gpu_ctx.msm(sc[:32 * n], pts) == (0, outs[0])
+    ps.close()

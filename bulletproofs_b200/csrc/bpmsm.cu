@@ -406,13 +406,15 @@ static int points_from_device(bp_ctx *c, const uint8_t *d_compressed, size_t n, 
     bp_points *h = new bp_points(); h->ctx = c; h->n = n;
     cudaError_t e = cudaMalloc((void **)&h->d_pts, n * sizeof(ge_niels));
     if (e != cudaSuccess) { c->err = std::string("cudaMalloc(points): ") + cudaGetErrorString(e); delete h; return BP_ERR_CUDA; }
-    CK(c, c->ok.ensure(n + 4));
-    uint32_t *d_bad = reinterpret_cast<uint32_t *>(c->ok.as<uint8_t>() + ((n + 3) & ~(size_t)3));
-    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n, 128), 128, 0, c->stream>>>(d_compressed, n, h->d_pts, c->ok.as<uint8_t>()));
-    std::vector<uint8_t> ok(n);
-    CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, n, cudaMemcpyDeviceToHost, c->stream)); CK(c, cudaStreamSynchronize(c->stream));
-    (void)d_bad;
-    for (uint8_t v : ok) if (!v) { cudaFree(h->d_pts); delete h; return BP_ERR_INVALID_POINT; }
+    int rc = [&]() -> int {
+        CK(c, c->ok.ensure(n));
+        LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n, 128), 128, 0, c->stream>>>(d_compressed, n, h->d_pts, c->ok.as<uint8_t>()));
+        std::vector<uint8_t> ok(n);
+        CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, n, cudaMemcpyDeviceToHost, c->stream)); CK(c, cudaStreamSynchronize(c->stream));
+        for (uint8_t v : ok) if (!v) return BP_ERR_INVALID_POINT;
+        return BP_OK;
+    }();
+    if (rc) { cudaFree(h->d_pts); delete h; return rc; }
     *out = h; return BP_OK;
 }
 int bp_points_create(bp_ctx *c, const uint8_t *points, size_t n, bp_points **out) {
@@ -1003,6 +1005,7 @@ struct bp_ippx {
     DevBuf a, b, cG, cH, gidx, hidx, scal, pidx, offs, in, outs;
 };
 extern "C" {
+static void ippx_free(bp_ippx *s);
 static int ippx_alloc(bp_ctx *c, size_t N, size_t B, bp_ippx **out) {
     if (!c || !out || N == 0 || (N & (N - 1)) || B == 0 || 2 * B * (N + 1) >= (1u << 31)) return BP_ERR_INVALID_ARGUMENT;      // power of two (inner_product_proof.rs:67)
     BUSY_CHECK(c);
@@ -1011,9 +1014,13 @@ static int ippx_alloc(bp_ctx *c, size_t N, size_t B, bp_ippx **out) {
     size_t BN = B * N;
     cudaError_t e = cudaMalloc((void **)&s->d_q, B * sizeof(ge_niels));
     if (e != cudaSuccess) { c->err = std::string("cudaMalloc(ippx): ") + cudaGetErrorString(e); delete s; return BP_ERR_CUDA; }
-    for (DevBuf *b : {&s->a, &s->b, &s->cG, &s->cH}) CK(c, b->ensure(BN * sizeof(sc)));
-    CK(c, s->gidx.ensure(N * 4)); CK(c, s->hidx.ensure(N * 4)); CK(c, s->scal.ensure(2 * B * (N + 1) * 32)); CK(c, s->pidx.ensure(2 * B * (N + 1) * 4));
-    CK(c, s->offs.ensure((2 * B + 1) * 4)); CK(c, s->in.ensure(std::max<size_t>(4 * BN * 32, 64 * B))); CK(c, s->outs.ensure(64 * B));
+    int rc = [&]() -> int {
+        for (DevBuf *b : {&s->a, &s->b, &s->cG, &s->cH}) CK(c, b->ensure(BN * sizeof(sc)));
+        CK(c, s->gidx.ensure(N * 4)); CK(c, s->hidx.ensure(N * 4)); CK(c, s->scal.ensure(2 * B * (N + 1) * 32)); CK(c, s->pidx.ensure(2 * B * (N + 1) * 4));
+        CK(c, s->offs.ensure((2 * B + 1) * 4)); CK(c, s->in.ensure(std::max<size_t>(4 * BN * 32, 64 * B))); CK(c, s->outs.ensure(64 * B));
+        return BP_OK;
+    }();
+    if (rc) { ippx_free(s); return rc; }
     *out = s; return BP_OK;
 }
 static void ippx_free(bp_ippx *s) {
@@ -1052,9 +1059,11 @@ int bp_ippx_begin(bp_ctx *c, bp_gens *gens, size_t n, size_t m, size_t n_proofs,
         idx[q] = (uint32_t)(2 + (q / n) * gens->cap + (q % n));
         idx[N + q] = (uint32_t)(2 + gens->parties * gens->cap + (q / n) * gens->cap + (q % n));
     }
-    CK(c, cudaMemcpyAsync(s->gidx.p, idx.data(), N * 4, cudaMemcpyHostToDevice, c->stream)); CK(c, cudaMemcpyAsync(s->hidx.p, idx.data() + N, N * 4, cudaMemcpyHostToDevice, c->stream));
-    CK(c, cudaStreamSynchronize(c->stream));
-    rc = ippx_load(s, Q, Gf, Hf, a, b);
+    rc = [&]() -> int {
+        CK(c, cudaMemcpyAsync(s->gidx.p, idx.data(), N * 4, cudaMemcpyHostToDevice, c->stream)); CK(c, cudaMemcpyAsync(s->hidx.p, idx.data() + N, N * 4, cudaMemcpyHostToDevice, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        return ippx_load(s, Q, Gf, Hf, a, b);
+    }();
     if (rc) { ippx_free(s); *out = nullptr; }
     return rc;
 }
@@ -1065,16 +1074,18 @@ int bp_ippx_begin_points(bp_ctx *c, const uint8_t *G, const uint8_t *H, size_t N
     cudaError_t e = cudaMalloc((void **)&s->own_pts, 2 * N * sizeof(ge_niels));
     if (e != cudaSuccess) { c->err = std::string("cudaMalloc(ippx points): ") + cudaGetErrorString(e); ippx_free(s); *out = nullptr; return BP_ERR_CUDA; }
     s->d_static = s->own_pts;
-    CK(c, c->in_points.ensure(2 * N * 32)); CK(c, c->ok.ensure(2 * N));
-    CK(c, cudaMemcpyAsync(c->in_points.p, G, N * 32, cudaMemcpyHostToDevice, st)); CK(c, cudaMemcpyAsync(c->in_points.as<uint8_t>() + N * 32, H, N * 32, cudaMemcpyHostToDevice, st));
-    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(2 * N, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), 2 * N, s->own_pts, c->ok.as<uint8_t>()));
     std::vector<uint8_t> ok(2 * N); std::vector<uint32_t> idx(2 * N);
     for (size_t q = 0; q < 2 * N; q++) idx[q] = (uint32_t)q;
-    CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, 2 * N, cudaMemcpyDeviceToHost, st));
-    CK(c, cudaMemcpyAsync(s->gidx.p, idx.data(), N * 4, cudaMemcpyHostToDevice, st)); CK(c, cudaMemcpyAsync(s->hidx.p, idx.data() + N, N * 4, cudaMemcpyHostToDevice, st));
-    CK(c, cudaStreamSynchronize(st));
-    for (uint8_t v : ok) if (!v) { ippx_free(s); *out = nullptr; return BP_ERR_INVALID_POINT; }
-    rc = ippx_load(s, Q, Gf, Hf, a, b);
+    rc = [&]() -> int {
+        CK(c, c->in_points.ensure(2 * N * 32)); CK(c, c->ok.ensure(2 * N));
+        CK(c, cudaMemcpyAsync(c->in_points.p, G, N * 32, cudaMemcpyHostToDevice, st)); CK(c, cudaMemcpyAsync(c->in_points.as<uint8_t>() + N * 32, H, N * 32, cudaMemcpyHostToDevice, st));
+        LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(2 * N, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), 2 * N, s->own_pts, c->ok.as<uint8_t>()));
+        CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, 2 * N, cudaMemcpyDeviceToHost, st));
+        CK(c, cudaMemcpyAsync(s->gidx.p, idx.data(), N * 4, cudaMemcpyHostToDevice, st)); CK(c, cudaMemcpyAsync(s->hidx.p, idx.data() + N, N * 4, cudaMemcpyHostToDevice, st));
+        CK(c, cudaStreamSynchronize(st));
+        for (uint8_t v : ok) if (!v) return BP_ERR_INVALID_POINT;
+        return ippx_load(s, Q, Gf, Hf, a, b);
+    }();
     if (rc) { ippx_free(s); *out = nullptr; }
     return rc;
 }

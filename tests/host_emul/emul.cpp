@@ -79,6 +79,9 @@ int emul_rp_scalars(const uint8_t *proof, uint32_t k, const uint8_t *V, uint32_t
     return 0;
 }
 
+int emul_pick_window(uint64_t avg_terms) { return msm_pick_window((size_t)avg_terms); }
+int emul_num_windows(int c) { return msm_num_windows(c); }
+
 // Pippenger bookkeeping exactly as the kernels do it (offset recoding, bucket sums, chunked suffix reduction, Horner)
 int emul_msm(const uint8_t *scalars, const uint8_t *points, uint32_t n, int c, uint32_t nthreads, uint8_t *out) {
     int W = msm_num_windows(c); uint32_t nb = 1u << (c - 1);

@@ -111,6 +111,20 @@ def test_pippenger_bookkeeping(E, orc):
         o = buf(); E.emul_msm(sc, pp, 6, c, 32, o); assert (0, o.raw) == orc.msm(sc, pp)
 
 
+def test_window_table(E):
+    """msm_pick_window: monotone in the MSM size, every window count covers 253 bits plus the recoding carry, and from 17 terms up
+    the width never divides 252 (a width that does leaves a carry-only top window whose single bucket receives half the terms)."""
+    import ctypes
+    E.emul_pick_window.argtypes = [ctypes.c_uint64]
+    prev = 0
+    for lg4 in range(0, 4 * 26):
+        n = int(2 ** (lg4 / 4))
+        c = E.emul_pick_window(n)
+        assert 3 <= c <= 16 and c >= prev; prev = c
+        assert E.emul_num_windows(c) * c >= 253
+        if n > 16: assert 252 % c != 0, (n, c)
+
+
 def test_verification_scalars_on_golden_proofs(E, orc, golden):
     """sum scalars * points of the device-side scalar assembly must be the identity for every golden
     proof (RangeProof::verify_multiple accepts) and must not be after a one-bit change."""

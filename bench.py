@@ -252,7 +252,6 @@ def main():
     ap.add_argument("--lg", type=int, default=16, help="--workload msm: terms per MSM = 2^lg")
     ap.add_argument("--msms", type=int, default=8, help="--workload msm: MSMs per call")
     ap.add_argument("--window", type=int, default=0, help="--workload msm: fix the Pippenger window (bits); 0 = by size")
-    ap.add_argument("--fp64-share", type=int, default=-1, help="eighths (0..8) of the decompression warps whose ladder runs on the FP64 pipe; -1 = the library's default")
     ap.add_argument("--check-lg", type=int, default=16, help="--workload msm: compare the first MSM with the CPU oracle up to this size")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -281,8 +280,6 @@ def main():
     plen = len(proofs) // BATCH
     streams = [torch.cuda.Stream(device=local) for _ in range(S)]
     ctxs = [bp.Context(local, stream=s.cuda_stream) for s in streams]
-    if args.fp64_share >= 0:
-        for c in ctxs: c.set_fp64_share(args.fp64_share)
 
     # generator table: derived once on rank 0, one NCCL broadcast over NVLink, imported by every context's table
     gens0 = bp.Gens(ctxs[0], N_BITS, M, empty=(rank != 0))

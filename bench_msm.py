@@ -81,8 +81,6 @@ def main(args, rank, world, local, local_world):
     ctx = bp.Context(local, stream=stream.cuda_stream)
     if getattr(args, "window", 0):
         ctx.set_msm_window(args.window)
-    if getattr(args, "fp64_share", -1) >= 0:
-        ctx.set_fp64_share(args.fp64_share)
     points = ctx.from_uniform_bytes(g_chain_uniform(n))                      # n x 32 B compressed, derived on the GPU
     # scalar pool: at least one call's worth, and more than L2
     T = M * n

@@ -25,7 +25,6 @@ SYMBOLS = {
     "bp_ctx_launch_count": (_c.c_uint64, [_vp]),
     "bp_ctx_synchronize": (_int, [_vp]),
     "bp_ctx_set_msm_window": (_int, [_vp, _int]),
-    "bp_ctx_set_fp64_share": (_int, [_vp, _int]),
     "bp_decompress_check_batch": (_int, [_vp, _u8p, _sz, _u8p]),
     "bp_from_uniform_bytes_batch": (_int, [_vp, _u8p, _sz, _u8p]),
     "bp_decompress_batch": (_int, [_vp, _u8p, _sz, _u8p, _u8p]),
@@ -233,10 +232,6 @@ class Context:
     def set_msm_window(self, bits: int):
         """Pippenger window of the generic MSM entry points: 0 = by size (default), 2..18 = fixed"""
         self._check(lib().bp_ctx_set_msm_window(self._h, bits))
-
-    def set_fp64_share(self, eighths: int):
-        """share (0..8 eighths) of the decompression warps whose 2^252-3 ladder runs on the FP64 pipe; set it before reserving a geometry"""
-        self._check(lib().bp_ctx_set_fp64_share(self._h, eighths))
 
     def prof_enable(self, on=True):
         self._check(lib().bp_prof_enable(self._h, 1 if on else 0))

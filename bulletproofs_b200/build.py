@@ -61,7 +61,7 @@ def build_emul(force=False):
     lib = os.path.join(edir, "libemul.so")
     srcs = [os.path.join(edir, "emul.cpp")] + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cuh")]
     if force or not _newer(lib, srcs):
-        _run(["g++", "-O2", "-std=c++17", "-pthread", "-frounding-math", "-ffp-contract=off", "-shared", "-fPIC", "-o", lib, os.path.join(edir, "emul.cpp")])
+        _run(["g++", "-O2", "-std=c++17", "-pthread", "-shared", "-fPIC", "-o", lib, os.path.join(edir, "emul.cpp")])
     return lib
 
 

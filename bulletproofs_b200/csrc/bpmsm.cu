@@ -50,7 +50,6 @@ struct bp_ctx {
     int device = 0, sm_count = 148; cudaStream_t stream = nullptr; bool own_stream = false;
     cudaStream_t aux = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;    // second branch of the verifier's launch graph
     std::string err; uint64_t launches = 0;
-    uint32_t fd_share = 0;                                    // eighths of the decompression warps whose ladder runs on the FP64 pipe (fd.cuh); bp_ctx_set_fp64_share
     int msm_window = 0;                                       // 0 = by size (msm_pick_window); bp_ctx_set_msm_window pins it (tuning / tests)
     bool prof_on = false; std::vector<ProfRec> prof;          // per-kernel CUDA-event timing (bp_prof_*)
     // MSM scratch
@@ -209,11 +208,11 @@ __global__ void k_rp_point_idx(rp_geom g, uint32_t gens_cap, uint32_t gens_parti
 }
 // decompress to the four extended coordinates (X, Y, Z = 1, T), 4 x 32 canonical bytes per point: the in-memory RistrettoPoint
 // a host caller keeps (bp_decompress_batch / bp_compress_batch)
-__global__ void __launch_bounds__(128) k_decompress_xyzt(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, uint8_t *__restrict__ ok, uint32_t fd_share) {
+__global__ void __launch_bounds__(128) k_decompress_xyzt(const uint8_t *__restrict__ in, size_t n, uint8_t *__restrict__ out, uint8_t *__restrict__ ok) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint8_t s[32]; ld32(s, in + 32 * i);
-    fe x, y; bool valid = ge_decode(x, y, s, decompress_on_fp64(fd_share));
+    fe x, y; bool valid = ge_decode(x, y, s);
     if (!valid) { x = fe_zero(); y = fe_one(); }
     uint8_t b[32];
     fe_tobytes(b, x); st32(out + 128 * i, b); fe_tobytes(b, y); st32(out + 128 * i + 32, b);
@@ -289,7 +288,6 @@ void bp_ctx_destroy(bp_ctx *c) {
 }
 const char *bp_last_error(const bp_ctx *c) { return c ? c->err.c_str() : "null context"; }
 uint64_t bp_ctx_launch_count(const bp_ctx *c) { return c ? c->launches : 0; }
-int bp_ctx_set_fp64_share(bp_ctx *c, int eighths) { if (!c || eighths < 0 || eighths > 8) return BP_ERR_INVALID_ARGUMENT; BUSY_CHECK(c); c->fd_share = (uint32_t)eighths; return BP_OK; }
 int bp_ctx_set_msm_window(bp_ctx *c, int window_bits) { if (!c || window_bits < 0 || window_bits > 18 || window_bits == 1) return BP_ERR_INVALID_ARGUMENT; c->msm_window = window_bits; return BP_OK; }
 int bp_ctx_synchronize(bp_ctx *c) { if (!c) return BP_ERR_INVALID_ARGUMENT; CK(c, cudaSetDevice(c->device)); CK(c, cudaStreamSynchronize(c->stream)); return BP_OK; }
 
@@ -300,7 +298,7 @@ int bp_decompress_check_batch(bp_ctx *c, const uint8_t *points, size_t n, uint8_
     CK(c, cudaSetDevice(c->device));
     CK(c, c->in_points.ensure(n * 32)); CK(c, c->niels.ensure(n * sizeof(ge_niels))); CK(c, c->ok.ensure(n));
     CK(c, cudaMemcpyAsync(c->in_points.p, points, n * 32, cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, c->niels.as<ge_niels>(), c->ok.as<uint8_t>(), c->fd_share));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, c->niels.as<ge_niels>(), c->ok.as<uint8_t>()));
     CK(c, cudaMemcpyAsync(ok, c->ok.p, n, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
     return BP_OK;
@@ -329,7 +327,7 @@ int bp_msm_batch_device(bp_ctx *c, const void *d_scalars, const void *d_points, 
     CK(c, c->niels.ensure((size_t)T * sizeof(ge_niels))); CK(c, c->ok.ensure(T)); CK(c, c->msm_err.ensure((size_t)M * 4)); CK(c, c->results.ensure((size_t)M * sizeof(ge_ext)));
     cudaStream_t s = c->stream;
     CK(c, cudaMemsetAsync(c->msm_err.p, 0, (size_t)M * 4, s));
-    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(T, 128), 128, 0, s>>>((const uint8_t *)d_points, T, c->niels.as<ge_niels>(), c->ok.as<uint8_t>(), c->fd_share));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(T, 128), 128, 0, s>>>((const uint8_t *)d_points, T, c->niels.as<ge_niels>(), c->ok.as<uint8_t>()));
     LAUNCH(c, KID_SMALL, k_mark_invalid<<<blocks_for(T, 256), 256, 0, s>>>(c->ok.as<uint8_t>(), (const uint32_t *)d_offsets_u32, M, T, c->msm_err.as<uint32_t>()));
     MsmArgs a{(const uint8_t *)d_scalars, (const uint32_t *)d_offsets_u32, M, T, nullptr, nullptr, c->niels.as<ge_niels>(), c->msm_err.as<uint32_t>(), 0};
     int rc = msm_core(c, a, c->results.as<ge_ext>());
@@ -381,7 +379,7 @@ int bp_decompress_batch(bp_ctx *c, const uint8_t *points, size_t n, uint8_t *xyz
     CK(c, cudaSetDevice(c->device));
     CK(c, c->in_points.ensure(n * 32)); CK(c, c->outs.ensure(n * 128)); CK(c, c->ok.ensure(n));
     CK(c, cudaMemcpyAsync(c->in_points.p, points, n * 32, cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(c, KID_DECOMPRESS, k_decompress_xyzt<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, c->outs.as<uint8_t>(), c->ok.as<uint8_t>(), c->fd_share));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress_xyzt<<<blocks_for(n, 128), 128, 0, c->stream>>>(c->in_points.as<uint8_t>(), n, c->outs.as<uint8_t>(), c->ok.as<uint8_t>()));
     CK(c, cudaMemcpyAsync(xyzt_out, c->outs.p, n * 128, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaMemcpyAsync(ok, c->ok.p, n, cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
@@ -410,7 +408,7 @@ static int points_from_device(bp_ctx *c, const uint8_t *d_compressed, size_t n, 
     if (e != cudaSuccess) { c->err = std::string("cudaMalloc(points): ") + cudaGetErrorString(e); delete h; return BP_ERR_CUDA; }
     int rc = [&]() -> int {
         CK(c, c->ok.ensure(n));
-        LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n, 128), 128, 0, c->stream>>>(d_compressed, n, h->d_pts, c->ok.as<uint8_t>(), c->fd_share));
+        LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n, 128), 128, 0, c->stream>>>(d_compressed, n, h->d_pts, c->ok.as<uint8_t>()));
         std::vector<uint8_t> ok(n);
         CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, n, cudaMemcpyDeviceToHost, c->stream)); CK(c, cudaStreamSynchronize(c->stream));
         for (uint8_t v : ok) if (!v) return BP_ERR_INVALID_POINT;
@@ -516,7 +514,7 @@ int bp_gens_create(bp_ctx *c, size_t cap, size_t parties, bp_gens **out) {
     CK(c, cudaMemcpyAsync(c->in_points.p, uni.data(), uni.size(), cudaMemcpyHostToDevice, s));
     CK(c, cudaMemcpyAsync(c->in_scalars.p, BASEPOINT, 32, cudaMemcpyHostToDevice, s));
     LAUNCH(c, KID_FROM_UNIFORM, k_from_uniform<<<blocks_for(g->n_points, 128), 128, 0, s>>>(c->in_points.as<uint8_t>(), g->n_points, g->d_table, nullptr));
-    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<1, 128, 0, s>>>(c->in_scalars.as<uint8_t>(), 1, g->d_table + 1, nullptr, c->fd_share));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<1, 128, 0, s>>>(c->in_scalars.as<uint8_t>(), 1, g->d_table + 1, nullptr));
     CK(c, cudaStreamSynchronize(s));
     return BP_OK;
 }
@@ -592,7 +590,6 @@ static uint64_t rp_ptr_signature(const bp_ctx *c) {
                             &c->rp_chal, &c->rp_tabs, &c->rp_raw, &c->pow2_tab, &c->ar_rp.counts, &c->ar_rp.starts, &c->ar_rp.cursor, &c->ar_rp.order, &c->ar_rp.sorted, &c->ar_rp.buckets, &c->ar_rp.wsums};
     uint64_t h = 1469598103934665603ULL;
     for (const DevBuf *b : bufs) { h ^= (uint64_t)(uintptr_t)b->p; h *= 1099511628211ULL; }
-    h ^= c->fd_share; h *= 1099511628211ULL;          // a kernel argument of the captured k_rp_decompress node
     return h;
 }
 // term -> point map and MSM offsets of the combined MSMs: depend only on the geometry, rebuilt when it changes
@@ -634,7 +631,7 @@ static int rp_chain(bp_ctx *c, bp_gens *gens, const rp_geom &g) {
         cudaStream_t keep = c->stream; c->stream = s2;          // LAUNCH brackets its events on ctx->stream
         int rc = [&]() -> int {
             const size_t dec_smem = (size_t)(RP_DEC_THREADS / g.D + 2) * (g.proof_len + 32 * g.m);
-            LAUNCH(c, KID_RP_DECOMPRESS, k_rp_decompress<<<blocks_for((size_t)total * g.D, RP_DEC_THREADS), RP_DEC_THREADS, dec_smem, s2>>>(par, g, total, c->rp_niels.as<ge_niels>(), c->rp_decbad.as<uint32_t>(), c->fd_share));
+            LAUNCH(c, KID_RP_DECOMPRESS, k_rp_decompress<<<blocks_for((size_t)total * g.D, RP_DEC_THREADS), RP_DEC_THREADS, dec_smem, s2>>>(par, g, total, c->rp_niels.as<ge_niels>(), c->rp_decbad.as<uint32_t>()));
             return BP_OK;
         }();
         c->stream = keep;
@@ -872,7 +869,7 @@ int bp_msm_indexed_batch(bp_ctx *c, bp_gens *gens, const uint8_t *scalars, const
     if (n_dyn) {
         CK(c, c->in_points.ensure(n_dyn * 32)); CK(c, c->niels.ensure(n_dyn * sizeof(ge_niels))); CK(c, c->ok.ensure(n_dyn));
         CK(c, cudaMemcpyAsync(c->in_points.p, dyn_points, n_dyn * 32, cudaMemcpyHostToDevice, s));
-        LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n_dyn, 128), 128, 0, s>>>(c->in_points.as<uint8_t>(), n_dyn, c->niels.as<ge_niels>(), c->ok.as<uint8_t>(), c->fd_share));
+        LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n_dyn, 128), 128, 0, s>>>(c->in_points.as<uint8_t>(), n_dyn, c->niels.as<ge_niels>(), c->ok.as<uint8_t>()));
         dyn_ok.resize(n_dyn);
         CK(c, cudaMemcpyAsync(dyn_ok.data(), c->ok.p, n_dyn, cudaMemcpyDeviceToHost, s));
     }
@@ -926,7 +923,7 @@ int bp_ipp_begin(bp_ctx *c, bp_gens *gens, size_t n, size_t m, const uint8_t Q[3
     CK(c, cudaMemcpyAsync(s->idx.p, idx.data(), 2 * N * 4, cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(c->in_points.p, Q, 32, cudaMemcpyHostToDevice, st));
     LAUNCH(c, KID_SMALL, k_gather_niels<<<blocks_for(2 * N, 128), 128, 0, st>>>(gens->d_table, s->idx.as<uint32_t>(), (uint32_t)(2 * N), s->pts));
-    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<1, 128, 0, st>>>(c->in_points.as<uint8_t>(), 1, s->pts + 2 * N, c->ok.as<uint8_t>(), c->fd_share));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<1, 128, 0, st>>>(c->in_points.as<uint8_t>(), 1, s->pts + 2 * N, c->ok.as<uint8_t>()));
     uint8_t ok = 0;
     CK(c, cudaMemcpyAsync(&ok, c->ok.p, 1, cudaMemcpyDeviceToHost, st)); CK(c, cudaStreamSynchronize(st));
     if (!ok) { cudaFree(s->pts); delete s; *out = nullptr; return BP_ERR_INVALID_POINT; }
@@ -941,7 +938,7 @@ int bp_ipp_begin_points(bp_ctx *c, const uint8_t *G, const uint8_t *H, size_t N,
     CK(c, cudaMemcpyAsync(c->in_points.p, G, N * 32, cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(c->in_points.as<uint8_t>() + N * 32, H, N * 32, cudaMemcpyHostToDevice, st));
     CK(c, cudaMemcpyAsync(c->in_points.as<uint8_t>() + 2 * N * 32, Q, 32, cudaMemcpyHostToDevice, st));
-    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n_pts, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), n_pts, s->pts, c->ok.as<uint8_t>(), c->fd_share));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(n_pts, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), n_pts, s->pts, c->ok.as<uint8_t>()));
     std::vector<uint8_t> ok(n_pts);
     CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, n_pts, cudaMemcpyDeviceToHost, st)); CK(c, cudaStreamSynchronize(st));
     for (uint8_t v : ok) if (!v) { cudaFree(s->pts); delete s; *out = nullptr; return BP_ERR_INVALID_POINT; }
@@ -1045,7 +1042,7 @@ static int ippx_load(bp_ippx *s, const uint8_t *Q, const uint8_t *Gf, const uint
                                                                          s->a.as<sc>(), s->b.as<sc>(), s->cG.as<sc>(), s->cH.as<sc>()));
     CK(c, c->in_points.ensure((size_t)s->B * 32)); CK(c, c->ok.ensure(s->B));
     CK(c, cudaMemcpyAsync(c->in_points.p, Q, (size_t)s->B * 32, cudaMemcpyHostToDevice, st));
-    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(s->B, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), s->B, s->d_q, c->ok.as<uint8_t>(), c->fd_share));
+    LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(s->B, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), s->B, s->d_q, c->ok.as<uint8_t>()));
     std::vector<uint8_t> ok(s->B);
     CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, s->B, cudaMemcpyDeviceToHost, st)); CK(c, cudaStreamSynchronize(st));
     for (uint8_t v : ok) if (!v) return BP_ERR_INVALID_POINT;
@@ -1082,7 +1079,7 @@ int bp_ippx_begin_points(bp_ctx *c, const uint8_t *G, const uint8_t *H, size_t N
     rc = [&]() -> int {
         CK(c, c->in_points.ensure(2 * N * 32)); CK(c, c->ok.ensure(2 * N));
         CK(c, cudaMemcpyAsync(c->in_points.p, G, N * 32, cudaMemcpyHostToDevice, st)); CK(c, cudaMemcpyAsync(c->in_points.as<uint8_t>() + N * 32, H, N * 32, cudaMemcpyHostToDevice, st));
-        LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(2 * N, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), 2 * N, s->own_pts, c->ok.as<uint8_t>(), c->fd_share));
+        LAUNCH(c, KID_DECOMPRESS, k_decompress<<<blocks_for(2 * N, 128), 128, 0, st>>>(c->in_points.as<uint8_t>(), 2 * N, s->own_pts, c->ok.as<uint8_t>()));
         CK(c, cudaMemcpyAsync(ok.data(), c->ok.p, 2 * N, cudaMemcpyDeviceToHost, st));
         CK(c, cudaMemcpyAsync(s->gidx.p, idx.data(), N * 4, cudaMemcpyHostToDevice, st)); CK(c, cudaMemcpyAsync(s->hidx.p, idx.data() + N, N * 4, cudaMemcpyHostToDevice, st));
         CK(c, cudaStreamSynchronize(st));
@@ -1205,11 +1202,6 @@ __global__ void k_debug_fe(int op, const uint8_t *a, const uint8_t *b, size_t n,
         case 4: r = fe_pow22523(x); break;
         case 5: r = fe_neg(x); break;
         case 7: r = fe_mul(fe_add(x, y), fe_sub(x, y)); break;      // chained, unreduced intermediates
-        case 8: r = fd_to_fe(fd_mul(fd_from_fe(x), fd_from_fe(y))); break;      // the FP64-pipe arithmetic of fd.cuh
-        case 9: r = fd_to_fe(fd_sqn(fd_from_fe(x), 1)); break;
-        case 10: r = fe_invert_fd(x); break;
-        case 11: r = fe_pow22523_fd(x); break;
-        case 12: { fd fx = fd_from_fe(x), fy = fd_from_fe(y); r = fd_to_fe(fd_mul(fd_sqn(fd_mul(fd_sqn(fd_mul(fx, fy), 1), fx), 20), fy)); break; }
         default: r = fe_sq(x);
     }
     uint8_t o[32]; fe_tobytes(o, r); st32(out + 32 * i, o);

@@ -10,7 +10,6 @@
 // thread = one point operation: a warp carries 32 independent bucket or point operations.
 #pragma once
 #include "fe.cuh"
-#include "fd.cuh"
 
 #define FE_D_LIMBS {0x135978a3u, 0x75eb4dcau, 0x4141d8abu, 0x00700a4du, 0x7779e898u, 0x8cc74079u, 0x2b6ffe73u, 0x52036ceeu}
 #define FE_D2_LIMBS {0x26b2f159u, 0xebd69b94u, 0x8283b156u, 0x00e0149au, 0xeef3d130u, 0x198e80f2u, 0x56dffce7u, 0x2406d9dcu}
@@ -88,12 +87,10 @@ BP_HD bool ge_ristretto_eq(const ge_ext &a, const ge_ext &b) {
 }
 
 // (was_square, r): r = sqrt(u/v) if u/v is square, else sqrt(i*u/v); r is the non-negative root
-// use_fd: run the 2^252-3 ladder on the FP64 pipe (fd.cuh) instead of the integer-multiply pipe; same value either way
-BP_HDN bool fe_sqrt_ratio_i(fe &r, const fe &u, const fe &v, bool use_fd = false) {
+BP_HDN bool fe_sqrt_ratio_i(fe &r, const fe &u, const fe &v) {
     fe v3 = fe_mul(fe_sq(v), v);
     fe v7 = fe_mul(fe_sq(v3), v);
-    fe w = fe_mul(u, v7);
-    fe rr = fe_mul(fe_mul(u, v3), use_fd ? fe_pow22523_fd(w) : fe_pow22523(w));
+    fe rr = fe_mul(fe_mul(u, v3), fe_pow22523(fe_mul(u, v7)));
     fe chk = fe_mul(v, fe_sq(rr));
     fe neg_u = fe_neg(u);
     bool ok = fe_eq(chk, u), flip = fe_eq(chk, neg_u), flip_i = fe_eq(chk, fe_mul(neg_u, fe_const_sqrt_m1()));
@@ -103,7 +100,7 @@ BP_HDN bool fe_sqrt_ratio_i(fe &r, const fe &u, const fe &v, bool use_fd = false
 }
 
 // decode 32 bytes; returns false for anything the reference's decompress() maps to None
-BP_HD bool ge_decode(fe &x, fe &y, const uint8_t s_bytes[32], bool use_fd = false) {
+BP_HD bool ge_decode(fe &x, fe &y, const uint8_t s_bytes[32]) {
     fe s = fe_frombytes_raw(s_bytes);
     fe sc = fe_canon(s);
     bool canonical = true;
@@ -113,7 +110,7 @@ BP_HD bool ge_decode(fe &x, fe &y, const uint8_t s_bytes[32], bool use_fd = fals
     fe ss = fe_sq(s), u1 = fe_sub(one, ss), u2 = fe_add(one, ss), u2s = fe_sq(u2);
     fe v = fe_sub(fe_neg(fe_mul(fe_const_d(), fe_sq(u1))), u2s);
     fe I;
-    bool ok = fe_sqrt_ratio_i(I, one, fe_mul(v, u2s), use_fd);
+    bool ok = fe_sqrt_ratio_i(I, one, fe_mul(v, u2s));
     fe dx = fe_mul(I, u2), dy = fe_mul(fe_mul(I, dx), v);
     x = fe_abs(fe_mul(fe_dbl(s), dx));
     y = fe_mul(u1, dy);

@@ -117,14 +117,8 @@ __device__ __forceinline__ void lds32(uint8_t dst[32], const uint8_t *smem_src) 
 }
 
 // ------------------------------------------------------------------ K1: batched Ristretto decompress
-// which warps of a decompression kernel run their 2^252-3 ladder on the FP64 pipe (fd.cuh): fd_share of every 8 consecutive warps,
-// interleaved (w * 5 mod 8 visits 0,5,2,7,4,1,6,3).  A warp takes one path or the other as a whole.
-__device__ __forceinline__ bool decompress_on_fp64(uint32_t fd_share) {
-    uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    return ((w * 5u) & 7u) < fd_share;
-}
 // in: n x 32 B compressed.  out: n affine-Niels points (identity when invalid), ok[i] in {0,1}.
-__global__ void __launch_bounds__(128) k_decompress(const uint8_t *__restrict__ in, size_t n, ge_niels *__restrict__ out, uint8_t *__restrict__ ok, uint32_t fd_share) {
+__global__ void __launch_bounds__(128) k_decompress(const uint8_t *__restrict__ in, size_t n, ge_niels *__restrict__ out, uint8_t *__restrict__ ok) {
     __shared__ __align__(128) uint8_t tile[128 * 32];
     __shared__ __align__(8) uint64_t bar;
     size_t base = (size_t)blockIdx.x * blockDim.x, i = base + threadIdx.x;
@@ -132,7 +126,7 @@ __global__ void __launch_bounds__(128) k_decompress(const uint8_t *__restrict__ 
     tma_stage_tile(tile, in + 32 * base, 32u * cnt, &bar);
     if (i >= n) return;
     uint8_t s[32]; lds32(s, tile + 32 * threadIdx.x);
-    fe x, y; bool valid = ge_decode(x, y, s, decompress_on_fp64(fd_share));
+    fe x, y; bool valid = ge_decode(x, y, s);
     ge_niels q = valid ? ge_to_niels_affine(x, y) : ge_niels_identity();
     st_niels(out + i, q);
     if (ok) ok[i] = valid ? 1 : 0;
@@ -717,7 +711,7 @@ __global__ void __launch_bounds__(128) k_rp_scalars(rp_geom g, const rp_head *__
 // block's 128 points come from are contiguous: they are staged with two TMA bulk copies, the 32-byte encodings are read from shared memory.
 #define RP_DEC_THREADS 128
 __global__ void __launch_bounds__(RP_DEC_THREADS, 5) k_rp_decompress(const rp_params *__restrict__ par, rp_geom g, uint32_t total,
-                                                                  ge_niels *__restrict__ out, uint32_t *__restrict__ dec_bad, uint32_t fd_share) {
+                                                                  ge_niels *__restrict__ out, uint32_t *__restrict__ dec_bad) {
     extern __shared__ __align__(128) uint8_t dec_smem[];
     __shared__ __align__(8) uint64_t bar;
     const size_t i0 = (size_t)blockIdx.x * blockDim.x, i = i0 + threadIdx.x, n_pts = (size_t)total * g.D;
@@ -732,7 +726,7 @@ __global__ void __launch_bounds__(RP_DEC_THREADS, 5) k_rp_decompress(const rp_pa
     else if (idx < 4 + 2 * g.k) src = proof + 224 + 64 * (idx - 4 - g.k) + 32;
     else src = sv + ((size_t)(p - pf) * g.m + (idx - 4 - 2 * g.k)) * 32;
     uint8_t s[32]; lds32(s, src);
-    fe x, y; bool valid = ge_decode(x, y, s, decompress_on_fp64(fd_share));
+    fe x, y; bool valid = ge_decode(x, y, s);
     st_niels(out + i, valid ? ge_to_niels_affine(x, y) : ge_niels_identity());
     if (!valid) dec_bad[p] = 1u;
 }

@@ -59,10 +59,6 @@ uint64_t bp_ctx_launch_count(const bp_ctx *ctx);
 /* Pippenger window size (bits) of the generic MSM entry points on this context: 0 = chosen by terms per MSM (default), 2..18 = fixed.
  * Results do not depend on it; tests use it to cover every window geometry, benchmarks to tune. */
 int bp_ctx_set_msm_window(bp_ctx *ctx, int window_bits);
-/* Share (in eighths, 0..8) of the point-decompression warps whose 2^252-3 ladder runs on the FP64 pipe instead of the integer-multiply
- * pipe (csrc/fd.cuh).  Results do not depend on it.  Takes effect for the next launch; a verification geometry reserved before the change runs by direct
- * launches until bp_rangeproof_verify_reserve is called again. */
-int bp_ctx_set_fp64_share(bp_ctx *ctx, int eighths);
 /* block until all work queued on the context's stream is finished */
 int bp_ctx_synchronize(bp_ctx *ctx);
 

@@ -2,7 +2,6 @@
 // with g++: the portable branches of the __host__ __device__ functions).  It lets the CPU-only
 // test tier check the limb algorithms, point formulas, transcript replay, verification scalars and
 // the Pippenger bookkeeping against the oracle without a GPU.  Nothing in the product links this.
-#include <cfenv>
 #include <cstring>
 #include <vector>
 #include "../../bulletproofs_b200/csrc/ge.cuh"
@@ -25,40 +24,6 @@ void emul_fe_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out) {
         default: r = fe_sq(x);
     }
     fe_tobytes(out, r);
-}
-// the FP64-pipe field arithmetic of fd.cuh (its host branch switches the rounding mode around the two round-toward-zero operations)
-static double fd_excess(const fd &x) {          // how far the limbs are above their width (loose bound: 2^14)
-    double m = 0;
-    for (int k = 0; k < 6; k++) { double e = x.v[k] - ((k & 1) ? 0x1p42 : 0x1p43); if (e > m) m = e; if (x.v[k] < 0) m = 1e300; }
-    return m;
-}
-double emul_fd_op(int op, const uint8_t *a, const uint8_t *b, uint8_t *out) {
-    fe x = fe_frombytes_raw(a), y = fe_frombytes_raw(b), r;
-    double ex = 0;
-    switch (op) {
-        case 0: { fd t = fd_mul(fd_from_fe(x), fd_from_fe(y)); ex = fd_excess(t); r = fd_to_fe(t); break; }
-        case 1: { fd t = fd_sq(fd_from_fe(x)); ex = fd_excess(t); r = fd_to_fe(t); break; }
-        case 2: r = fe_invert_fd(x); break;
-        case 3: r = fe_pow22523_fd(x); break;
-        case 4: r = fd_to_fe(fd_from_fe(x)); break;
-        default: {                               // chains over loosely normalised intermediates: ((x*y)^2 * x)^(2^20) * y
-            fd fx = fd_from_fe(x), fy = fd_from_fe(y);
-            fd t = fd_mul(fd_sqn(fd_mul(fd_sq(fd_mul(fx, fy)), fx), 20), fy); ex = fd_excess(t); r = fd_to_fe(t);
-        }
-    }
-    fe_tobytes(out, r);
-    return ex;
-}
-// the same on raw limbs (lets the test drive the loose-normalisation bound 2^width + 2^14 to its edge)
-double emul_fd_raw(int op, const uint64_t *a, const uint64_t *b, uint8_t *out) {
-    fd x, y; for (int k = 0; k < 6; k++) { x.v[k] = (double)a[k]; y.v[k] = (double)b[k]; }
-    fd t = op == 0 ? fd_mul(x, y) : fd_sq(x);
-    fe_tobytes(out, fd_to_fe(t));
-    return fd_excess(t);
-}
-int emul_point_roundtrip_fd(const uint8_t *in, uint8_t *out) {
-    fe x, y; if (!ge_decode(x, y, in, true)) return 0;
-    ge_encode(out, ge_from_niels(ge_to_niels_affine(x, y))); return 1;
 }
 int emul_point_roundtrip(const uint8_t *in, uint8_t *out) {
     fe x, y; if (!ge_decode(x, y, in)) return 0;

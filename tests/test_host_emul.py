@@ -111,44 +111,6 @@ def test_pippenger_bookkeeping(E, orc):
         o = buf(); E.emul_msm(sc, pp, 6, c, 32, o); assert (0, o.raw) == orc.msm(sc, pp)
 
 
-def test_fp64_field_arithmetic(E, orc):
-    """csrc/fd.cuh (six 42.5-bit limbs in doubles, products split by FMAs under round-toward-zero) against Python integers: conversions,
-    squaring, multiplication, chains over loosely normalised intermediates, the inversion and 2^252-3 ladders, raw limbs at the edge of
-    the loose bound, and point decompression through the FP64 ladder."""
-    E.emul_fd_op.restype = ctypes.c_double; E.emul_fd_raw.restype = ctypes.c_double
-    def op(o, a, b=0):
-        out = buf(); ex = E.emul_fd_op(o, le(a), le(b), out); assert ex < 2**14
-        return int.from_bytes(out.raw, "little")
-    rnd = random.Random(21)
-    ones43 = sum(((1 << 43) - 1) << s for s in (0, 85, 170)); ones42 = sum(((1 << 42) - 1) << s for s in (43, 128, 213))
-    edge = [0, 1, 2, 19, p - 1, p, p + 1, 2**255 - 1, 2**255, 2**255 + 18, 2**256 - 1, 2**256 - 38, 2**43 - 1, 2**43, 2**85 - 1, (1 << 255) - (1 << 213), ones43, ones42, ones43 | ones42]
-    vals = edge + [rnd.randrange(2**256) for _ in range(150)]
-    for a in vals:
-        assert op(4, a) == a % p
-        assert op(1, a) == a * a % p
-        for b in rnd.sample(vals, 4):
-            assert op(0, a, b) == a * b % p
-            assert op(9, a, b) == pow(pow(a * b, 2, p) * a, 2**20, p) * b % p
-    for a in vals[:40]:
-        assert op(2, a) == pow(a, p - 2, p)
-        assert op(3, a) == pow(a, (p - 5) // 8, p)
-    W = [43, 42, 43, 42, 43, 42]; POS = [0, 43, 85, 128, 170, 213]
-    val = lambda limbs: sum(x << s for x, s in zip(limbs, POS))
-    def raw(o, la, lb):
-        out = buf(); ex = E.emul_fd_raw(o, (ctypes.c_uint64 * 6)(*la), (ctypes.c_uint64 * 6)(*lb), out); assert ex < 2**14
-        return int.from_bytes(out.raw, "little")
-    cases = [[(1 << w) + (1 << 14) - 1 for w in W], [0] * 6, [1] + [0] * 5]
-    cases += [[rnd.choice([0, 1, (1 << w) - 1, (1 << w) + (1 << 14) - 1, rnd.randrange((1 << w) + (1 << 14))]) for w in W] for _ in range(1500)]
-    for la in cases:
-        assert raw(1, la, la) == val(la) ** 2 % p
-        lb = rnd.choice(cases); assert raw(0, la, lb) == val(la) * val(lb) % p
-    for i in range(60):
-        enc = orc.from_uniform(rnd.randbytes(64)) if i % 3 else rnd.randbytes(32)
-        o1, o2 = buf(), buf()
-        r1, r2 = E.emul_point_roundtrip(enc, o1), E.emul_point_roundtrip_fd(enc, o2)
-        assert r1 == r2 == (1 if orc.point_is_valid(enc) else 0) and (r1 == 0 or o1.raw == o2.raw == enc)
-
-
 def test_window_table(E):
     """msm_pick_window: monotone in the MSM size, every window count covers 253 bits plus the recoding carry, and from 17 terms up
     the width never divides 252 (a width that does leaves a carry-only top window whose single bucket receives half the terms)."""

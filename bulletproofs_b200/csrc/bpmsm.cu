@@ -37,7 +37,7 @@ const char *const KERNEL_NAMES[KID_COUNT] = {"k_decompress", "k_compress", "k_fr
 struct ProfRec { int kid; cudaEvent_t a, b; };
 
 struct VerifyState {          // what bp_rangeproof_verify_*begin leaves for *_finish
-    bool active = false; rp_geom g{}; uint32_t total = 0; bp_gens *gens = nullptr; uint8_t param_verdict = 0;
+    bool active = false; rp_geom g{}; uint32_t total = 0, n_batches = 1; bp_gens *gens = nullptr; uint8_t param_verdict = 0;
 };
 struct MsmArena { DevBuf counts, starts, cursor, order, sorted, buckets, wsums; };      // scratch of one Pippenger pipeline pass
 struct MsmPlan { int c = 0, W = 0; uint32_t nb = 0, heavy_min = 0; size_t segs = 0, n_buckets = 0, heavy_cap = 0; uint32_t n_msm = 0, T = 0; };
@@ -723,6 +723,29 @@ static int rp_verify_fallback(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32
     return BP_OK;
 }
 
+// Kernel-node priorities of the captured graph.  With several groups in flight the block scheduler picks among the pending blocks of every
+// running graph; policy 1 lets the two kernels that fill the machine (decompression, bucket accumulation) go first, policy 2 the latency-bound
+// stages.  0 leaves every node at the stream's priority.  BP_GRAPH_PRIORITY selects (tuning experiment, profiles/r2_experiments.md §7).
+static void rp_graph_priorities(cudaGraph_t graph, int policy) {
+    if (policy != 1 && policy != 2) return;
+    int least = 0, greatest = 0;
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess || least == greatest) return;
+    size_t n = 0;
+    if (cudaGraphGetNodes(graph, nullptr, &n) != cudaSuccess || n == 0) return;
+    std::vector<cudaGraphNode_t> nodes(n);
+    if (cudaGraphGetNodes(graph, nodes.data(), &n) != cudaSuccess) return;
+    for (size_t i = 0; i < n; i++) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams p;
+        if (cudaGraphKernelNodeGetParams(nodes[i], &p) != cudaSuccess) continue;
+        const bool wide = p.func == (void *)k_rp_decompress || p.func == (void *)k_msm_accumulate<1> || p.func == (void *)k_msm_accumulate<2>;
+        cudaLaunchAttributeValue v; memset(&v, 0, sizeof v);
+        v.priority = (wide == (policy == 1)) ? greatest : least;
+        cudaGraphKernelNodeSetAttribute(nodes[i], cudaLaunchAttributePriority, &v);
+    }
+    cudaGetLastError();
+}
 int bp_rangeproof_verify_reserve(bp_ctx *c, bp_gens *gens, size_t n, size_t m, size_t count, size_t n_batches) {
     if (!c || !gens) return BP_ERR_INVALID_ARGUMENT;
     BUSY_CHECK(c);
@@ -745,7 +768,9 @@ int bp_rangeproof_verify_reserve(bp_ctx *c, bp_gens *gens, size_t n, size_t m, s
     c->graph_launches = c->launches - l0; c->launches = l0;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) { c->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return BP_ERR_CUDA; }
-    e = cudaGraphInstantiate(&c->graph, graph, 0);
+    const char *pol_env = getenv("BP_GRAPH_PRIORITY"); const int pol = pol_env ? atoi(pol_env) : 0;
+    rp_graph_priorities(graph, pol);
+    e = cudaGraphInstantiate(&c->graph, graph, (pol == 1 || pol == 2) ? cudaGraphInstantiateFlagUseNodePriority : 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { c->graph = nullptr; c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return BP_ERR_CUDA; }
     size_t key[6] = {g.n, g.m, g.count, g.nbatch, (size_t)(uintptr_t)gens, g.proof_len};
@@ -767,7 +792,7 @@ int bp_rangeproof_verify_group_begin(bp_ctx *c, bp_gens *gens, const uint8_t *tr
     CK(c, cudaSetDevice(c->device));
     rp_geom g{};
     uint8_t pv = rp_param_verdict(gens, proof_len, n, m, &g);
-    VerifyState vs; vs.total = (uint32_t)(count * n_batches); vs.gens = gens; vs.param_verdict = pv;
+    VerifyState vs; vs.total = (uint32_t)(count * n_batches); vs.n_batches = (uint32_t)n_batches; vs.gens = gens; vs.param_verdict = pv;
     if (pv != BP_PROOF_OK) { vs.active = true; c->vs = vs; return BP_OK; }     // the whole call gets this verdict in _finish
     if (!rp_set_group(&g, count, n_batches)) return BP_ERR_INVALID_ARGUMENT;
     vs.g = g;
@@ -787,7 +812,7 @@ int bp_rangeproof_verify_group_begin(bp_ctx *c, bp_gens *gens, const uint8_t *tr
 int bp_rangeproof_verify_group_finish(bp_ctx *c, uint8_t *verdicts, uint8_t *batch_ok) {
     if (!c || !verdicts || !c->vs.active) return BP_ERR_INVALID_ARGUMENT;
     VerifyState vs = c->vs; c->vs.active = false;
-    if (vs.param_verdict != BP_PROOF_OK) { memset(verdicts, (int)vs.param_verdict, vs.total); if (batch_ok) memset(batch_ok, 0, 1); return BP_OK; }
+    if (vs.param_verdict != BP_PROOF_OK) { memset(verdicts, (int)vs.param_verdict, vs.total); if (batch_ok) memset(batch_ok, 0, vs.n_batches); return BP_OK; }
     CK(c, cudaSetDevice(c->device));
     CK(c, cudaStreamSynchronize(c->stream));
     bool redo = false, contrib_ready = false;

@@ -500,7 +500,7 @@ def verify_group(ctx: Context, gens: Gens, transcript: Transcript, proofs: bytes
     proof_len = rangeproof_size(n, m)
     if len(proofs) != proof_len * count * n_batches or len(commitments) != 32 * m * count * n_batches:
         raise BpError(ERR_LENGTH_MISMATCH, "proof/commitment buffer sizes")
-    verdicts = ctypes.create_string_buffer(count * n_batches); ok = ctypes.create_string_buffer(n_batches)
+    verdicts = ctypes.create_string_buffer(count * n_batches); ok = ctypes.create_string_buffer(b"\xff" * n_batches, n_batches)      # every flag is written by _finish
     ctx._check(lib().bp_rangeproof_verify_group_begin(ctx._h, gens._h, transcript.to_bytes(), proofs, proof_len, commitments, n, m, count, n_batches, seed))
     ctx._check(lib().bp_rangeproof_verify_group_finish(ctx._h, verdicts, ok))
     return list(verdicts.raw), list(ok.raw)

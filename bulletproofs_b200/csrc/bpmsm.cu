@@ -723,29 +723,6 @@ static int rp_verify_fallback(bp_ctx *c, bp_gens *gens, const rp_geom &g, uint32
     return BP_OK;
 }
 
-// Kernel-node priorities of the captured graph.  With several groups in flight the block scheduler picks among the pending blocks of every
-// running graph; policy 1 lets the two kernels that fill the machine (decompression, bucket accumulation) go first, policy 2 the latency-bound
-// stages.  0 leaves every node at the stream's priority.  BP_GRAPH_PRIORITY selects (tuning experiment, profiles/r2_experiments.md §7).
-static void rp_graph_priorities(cudaGraph_t graph, int policy) {
-    if (policy != 1 && policy != 2) return;
-    int least = 0, greatest = 0;
-    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess || least == greatest) return;
-    size_t n = 0;
-    if (cudaGraphGetNodes(graph, nullptr, &n) != cudaSuccess || n == 0) return;
-    std::vector<cudaGraphNode_t> nodes(n);
-    if (cudaGraphGetNodes(graph, nodes.data(), &n) != cudaSuccess) return;
-    for (size_t i = 0; i < n; i++) {
-        cudaGraphNodeType t;
-        if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
-        cudaKernelNodeParams p;
-        if (cudaGraphKernelNodeGetParams(nodes[i], &p) != cudaSuccess) continue;
-        const bool wide = p.func == (void *)k_rp_decompress || p.func == (void *)k_msm_accumulate<1> || p.func == (void *)k_msm_accumulate<2>;
-        cudaLaunchAttributeValue v; memset(&v, 0, sizeof v);
-        v.priority = (wide == (policy == 1)) ? greatest : least;
-        cudaGraphKernelNodeSetAttribute(nodes[i], cudaLaunchAttributePriority, &v);
-    }
-    cudaGetLastError();
-}
 int bp_rangeproof_verify_reserve(bp_ctx *c, bp_gens *gens, size_t n, size_t m, size_t count, size_t n_batches) {
     if (!c || !gens) return BP_ERR_INVALID_ARGUMENT;
     BUSY_CHECK(c);
@@ -768,9 +745,7 @@ int bp_rangeproof_verify_reserve(bp_ctx *c, bp_gens *gens, size_t n, size_t m, s
     c->graph_launches = c->launches - l0; c->launches = l0;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) { c->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return BP_ERR_CUDA; }
-    const char *pol_env = getenv("BP_GRAPH_PRIORITY"); const int pol = pol_env ? atoi(pol_env) : 0;
-    rp_graph_priorities(graph, pol);
-    e = cudaGraphInstantiate(&c->graph, graph, (pol == 1 || pol == 2) ? cudaGraphInstantiateFlagUseNodePriority : 0);
+    e = cudaGraphInstantiate(&c->graph, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) { c->graph = nullptr; c->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return BP_ERR_CUDA; }
     size_t key[6] = {g.n, g.m, g.count, g.nbatch, (size_t)(uintptr_t)gens, g.proof_len};

@@ -208,6 +208,10 @@ def test_verify_parameter_errors(gpu_ctx, orc, golden):
         want = orc.rangeproof_verify(og, ot, proof, vc[:32 * m], m, n)
         got = bp.verify_batch(gpu_ctx, gens, t, proof, vc[:32 * m], n, m, 1, proof_len=len(proof))
         assert got == [want], (n, m, len(proof), got, want)
+    # a launch group whose parameters are rejected: every proof gets the code, every batch flag is cleared
+    want = orc.rangeproof_verify(og, ot, by[(64, 1)], vc[:32], 1, 64)
+    got, ok = bp.verify_group(gpu_ctx, gens, t, by[(64, 1)] * 6, vc[:32] * 6, 64, 1, 2, 3)
+    assert want != 0 and got == [want] * 6 and ok == [0, 0, 0]
     gens.close()
 
 

@@ -9,6 +9,16 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
+# BP_TEST_MOCK_ENGINE=1 (set only by tests/test_host_mirror_cpu.py for its child process): the C++ host mirror and the Python binding run
+# against tests/mock_engine (the oracle's CPU arithmetic behind the same C ABI), so that the mirror's own logic is exercised without a GPU.
+# The product never does this: bulletproofs_b200 loads libbpmsm.so only.
+MOCK_ENGINE = os.environ.get("BP_TEST_MOCK_ENGINE") == "1"
+if MOCK_ENGINE:
+    import bulletproofs_b200 as _bp
+    _bp.LIB_PATH = os.path.join(ROOT, "tests", "mock_engine", "libmockbpmsm.so")
+    _bp.HOST_LIB_PATH = os.path.join(ROOT, "tests", "mock_engine", "libbulletproofs_host_mock.so")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
@@ -21,6 +31,9 @@ def built():
     b.build_emul()
     b.build_cuda()
     b.build_host()
+    sys.path.insert(0, os.path.join(ROOT, "tests", "mock_engine"))
+    import build_mock
+    build_mock.build_mock_engine()
     return True
 
 

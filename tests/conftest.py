@@ -31,9 +31,10 @@ def built():
     b.build_emul()
     b.build_cuda()
     b.build_host()
-    sys.path.insert(0, os.path.join(ROOT, "tests", "mock_engine"))
-    import build_mock
-    build_mock.build_mock_engine()
+    if MOCK_ENGINE:
+        sys.path.insert(0, os.path.join(ROOT, "tests", "mock_engine"))
+        import build_mock
+        build_mock.build_mock_engine()
     return True
 
 

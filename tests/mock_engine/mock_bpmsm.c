@@ -96,7 +96,10 @@ int bp_decompress_check_batch(bp_ctx *c, const uint8_t *points, size_t n, uint8_
     for (size_t i = 0; i < n; i++) { ge p; ok[i] = ge_decode(&p, points + 32 * i) ? 1 : 0; }
     TIMED_END; return BP_OK;
 }
-static void msm_ge(uint8_t out[32], const sc *s, const ge *p, size_t n) { ge r; ge_msm_vartime(&r, s, p, n); ge_encode(out, &r); }
+/* BP_MOCK_SKIP_POINT_MATH=1 (tests/mock_engine/profile_mirror.py only): every point result is the first input point, so that a profile of
+ * the mirror is not drowned in the mock's own curve arithmetic.  The outputs are then meaningless (proofs do not verify). */
+static int skip_math(void) { static int f = -1; if (f < 0) f = getenv("BP_MOCK_SKIP_POINT_MATH") != NULL; return f; }
+static void msm_ge(uint8_t out[32], const sc *s, const ge *p, size_t n) { ge r; if (skip_math() && n) r = p[0]; else ge_msm_vartime(&r, s, p, n); ge_encode(out, &r); }
 
 int bp_msm_batch(bp_ctx *c, const uint8_t *scalars, const uint8_t *points, const uint64_t *offsets, size_t n_msm, uint8_t *outs, uint8_t *status) {
     if (!c || !offsets || !outs || n_msm == 0) return BP_ERR_INVALID_ARGUMENT;
@@ -185,7 +188,7 @@ int bp_ipp_lr(bp_ipp *s, size_t h, const uint8_t *sL, const uint8_t *sR, uint8_t
     free(sc_); free(p);
     TIMED_END; return rc;
 }
-static void lincomb2(ge *out, const sc *x, const ge *P, const sc *y, const ge *Q) { sc s[2] = {*x, *y}; ge p[2] = {*P, *Q}; ge_msm_vartime(out, s, p, 2); }
+static void lincomb2(ge *out, const sc *x, const ge *P, const sc *y, const ge *Q) { if (skip_math()) { *out = *P; return; } sc s[2] = {*x, *y}; ge p[2] = {*P, *Q}; ge_msm_vartime(out, s, p, 2); }
 int bp_ipp_fold(bp_ipp *s, size_t h, const uint8_t *g_lo, const uint8_t *g_hi, const uint8_t *h_lo, const uint8_t *h_hi, int per_index) {
     if (!s || !g_lo || !g_hi || !h_lo || !h_hi || h == 0 || 2 * h > s->N) return BP_ERR_INVALID_ARGUMENT;
     TIMED_BEGIN;

@@ -15,6 +15,9 @@ MIRROR_TESTS = ["tests/test_gpu_prover.py", "tests/test_linear_proof.py", "tests
 
 
 def test_host_mirror_against_oracle_through_the_mock_engine(built):
+    sys.path.insert(0, os.path.join(ROOT, "tests", "mock_engine"))
+    import build_mock
+    build_mock.build_mock_engine()
     env = dict(os.environ, BP_TEST_MOCK_ENGINE="1")
     # the two largest R1CS sizes are left to the GPU tier (the mock's MSMs are single-threaded CPU code)
     r = subprocess.run([sys.executable, "-m", "pytest"] + MIRROR_TESTS + ["-m", "gpu", "-x", "-q", "-k", "not config5", "-p", "no:cacheprovider"],
